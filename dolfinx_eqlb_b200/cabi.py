@@ -1,0 +1,160 @@
+"""ctypes mirror of `include/eqlb_b200.h` (structs + library loader).
+
+This is the Python stand-in for the reference's pybind11 layer
+(`python/dolfinx_eqlb/wrappers.cpp`): it turns mesh/table objects into the plain
+C structs of the C ABI.  The product library is `csrc/libeqlb_b200.so`; there is
+no fallback - loading fails loudly when the CUDA library has not been built.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libeqlb_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int8_p = C.POINTER(C.c_int8)
+c_uint8_p = C.POINTER(C.c_uint8)
+c_uint32_p = C.POINTER(C.c_uint32)
+
+
+class EqlbMesh(C.Structure):
+    _fields_ = [
+        ("nnode", C.c_int32),
+        ("ncell", C.c_int32),
+        ("nfct", C.c_int32),
+        ("x", c_double_p),
+        ("cell_node", c_int32_p),
+        ("cell_fct", c_int32_p),
+        ("fct_node", c_int32_p),
+        ("fct_cell_off", c_int32_p),
+        ("fct_cell", c_int32_p),
+        ("node_cell_off", c_int32_p),
+        ("node_cell", c_int32_p),
+        ("node_fct_off", c_int32_p),
+        ("node_fct", c_int32_p),
+        ("fct_perms", c_uint8_p),
+        ("cell_perm_info", c_uint32_p),
+        ("dg_dofmap", c_int32_p),
+    ]
+
+
+_TABLE_DOUBLES = ["qpts", "qwts", "fpts_s", "fwts", "M", "rt_q", "rt_f", "dg_q", "dg_f", "hat_q", "hat_f", "trafo"]
+_TABLE_INTS = ["fct_closure", "div_lm"]
+_TABLE_REF = ["rt_mass", "fct_mom", "cell_mom_f", "cell_mom_g", "bc_mat", "rt_p1"]
+
+
+class EqlbTables(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ["k", "p", "nrt", "ndg", "ndg_fct", "nq", "nqf", "ndiv", "nadd"]]
+        + [(n, c_double_p) for n in _TABLE_DOUBLES]
+        + [(n, c_int32_p) for n in _TABLE_INTS]
+        + [(n, c_double_p) for n in _TABLE_REF]
+    )
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class PackedMesh:
+    """Owns contiguous copies of the mesh arrays and the C struct view."""
+
+    def __init__(self, mesh, ndg):
+        from .mesh import dg_dofmap
+
+        self.mesh = mesh
+        self._keep = {}
+
+        def keep(name, arr, dt):
+            a = np.ascontiguousarray(arr, dtype=dt)
+            self._keep[name] = a
+            return a
+
+        s = EqlbMesh()
+        s.nnode, s.ncell, s.nfct = mesh.nnode, mesh.ncell, mesh.nfct
+        s.x = _ptr(keep("x", mesh.x, np.float64), C.c_double)
+        for name in ["cell_node", "cell_fct", "fct_node", "fct_cell_off", "fct_cell", "node_cell_off", "node_cell", "node_fct_off", "node_fct"]:
+            setattr(s, name, _ptr(keep(name, getattr(mesh, name), np.int32), C.c_int32))
+        s.fct_perms = _ptr(keep("fct_perms", mesh.fct_perms, np.uint8), C.c_uint8)
+        s.cell_perm_info = _ptr(keep("cell_perm_info", mesh.cell_perm_info, np.uint32), C.c_uint32)
+        s.dg_dofmap = _ptr(keep("dg_dofmap", dg_dofmap(mesh.ncell, ndg), np.int32), C.c_int32)
+        self.struct = s
+
+
+class PackedTables:
+    def __init__(self, tables):
+        self.tables = tables
+        self._keep = {}
+        s = EqlbTables()
+        for n in ["k", "p", "nrt", "ndg", "ndg_fct", "nq", "nqf", "ndiv", "nadd"]:
+            setattr(s, n, getattr(tables, n))
+        for n in _TABLE_DOUBLES + _TABLE_REF:
+            a = np.ascontiguousarray(getattr(tables, n), dtype=np.float64)
+            self._keep[n] = a
+            setattr(s, n, _ptr(a, C.c_double))
+        for n in _TABLE_INTS:
+            a = np.ascontiguousarray(getattr(tables, n), dtype=np.int32)
+            if a.size == 0:
+                a = np.zeros(2, dtype=np.int32)
+            self._keep[n] = a
+            setattr(s, n, _ptr(a, C.c_int32))
+        self.struct = s
+
+
+def ptr_array(arrays, ctype=C.c_double):
+    """Array of pointers (e.g. `const double* const*`) from a list of numpy arrays
+    (entries may be None -> NULL)."""
+    PT = C.POINTER(ctype)
+    arr = (PT * len(arrays))()
+    for i, a in enumerate(arrays):
+        arr[i] = _ptr(a, ctype) if a is not None else PT()
+    return arr
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA product library; raise loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"CUDA extension {LIB_PATH} not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.eqlb_create.argtypes = [C.POINTER(EqlbMesh), C.POINTER(EqlbTables), C.c_int, C.c_uint32, C.POINTER(H)]
+    lib.eqlb_create.restype = C.c_int
+    lib.eqlb_destroy.argtypes = [H]
+    lib.eqlb_destroy.restype = None
+    lib.eqlb_set_stream.argtypes = [H, C.c_void_p]
+    lib.eqlb_set_stream.restype = C.c_int
+    lib.eqlb_set_bcs.argtypes = [H, c_int8_p, C.POINTER(c_double_p), c_int8_p, c_int8_p]
+    lib.eqlb_set_bcs.restype = C.c_int
+    lib.eqlb_se_run.argtypes = [H, C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p), c_double_p, C.c_int]
+    lib.eqlb_se_run.restype = C.c_int
+    lib.eqlb_ev_run.argtypes = [H, C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int]
+    lib.eqlb_ev_run.restype = C.c_int
+    lib.eqlb_local_project.argtypes = [H, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int]
+    lib.eqlb_local_project.restype = C.c_int
+    lib.eqlb_patch_dims.argtypes = [H, c_int32_p, c_int32_p, c_int32_p]
+    lib.eqlb_patch_dims.restype = C.c_int
+    lib.eqlb_get_patch_maps.argtypes = [H, c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int8_p, c_int8_p, c_uint8_p, c_uint8_p, c_int32_p]
+    lib.eqlb_get_patch_maps.restype = C.c_int
+    lib.eqlb_get_se_dofmaps.argtypes = [H, c_int32_p, c_int32_p, c_int8_p, c_int32_p, c_int32_p]
+    lib.eqlb_get_se_dofmaps.restype = C.c_int
+    lib.eqlb_launch_count.argtypes = [H]
+    lib.eqlb_launch_count.restype = C.c_int64
+    lib.eqlb_last_error.restype = C.c_char_p
+    lib.eqlb_version.restype = C.c_char_p
+    _lib = lib
+    return lib

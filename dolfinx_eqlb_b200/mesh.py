@@ -1,0 +1,216 @@
+"""Synthetic triangle meshes + the topology arrays the hot path reads.
+
+The reference reads these arrays from DOLFINx 0.6.0 (`se/Patch.cpp:23-28`,
+`se/reconstruction.hpp:83-93`, `se/solve_patch_semiexplt.hpp:223-224`,
+`ev/reconstruction.hpp:79-107`).  DOLFINx is not available offline, so this
+module produces arrays with the same *meaning*, with a fixed, documented
+numbering:
+
+* facet f of a cell is opposite local vertex f; `cell_fct[c, f]`
+* facets are numbered by lexicographically sorted (min, max) vertex pair
+* `fct_cell`, `node_cell`, `node_fct` adjacency lists are ascending
+* `fct_perms[c*3+f] = 1` iff the two local vertices of facet f appear in
+  descending global order in cell c (DOLFINx facet reflection bit)
+* boundary ids follow `python/test/unit/utils.py:74-79`:
+  1: x=0, 2: y=0, 3: x=1, 4: y=1
+
+Everything is vectorised numpy so that the 1024^2 crossed mesh (4.2 M cells)
+builds in seconds.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+FACET_VERTS = np.array([[1, 2], [0, 2], [0, 1]], dtype=np.int32)
+
+
+@dataclass
+class Mesh:
+    x: np.ndarray  # [nnode][3] f64
+    cell_node: np.ndarray  # [ncell][3] i32 (also geometry dofmap)
+    cell_fct: np.ndarray  # [ncell][3] i32
+    fct_node: np.ndarray  # [nfct][2] i32 (min, max)
+    fct_cell_off: np.ndarray  # [nfct+1] i32
+    fct_cell: np.ndarray  # CSR data i32
+    node_cell_off: np.ndarray  # [nnode+1] i32
+    node_cell: np.ndarray
+    node_fct_off: np.ndarray  # [nnode+1] i32
+    node_fct: np.ndarray
+    fct_perms: np.ndarray  # [ncell*3] u8
+    cell_perm_info: np.ndarray  # [ncell] u32
+    bfct: np.ndarray  # boundary facet ids (ascending)
+    bfct_side: np.ndarray  # boundary id 1..4 (0 if not on the unit-square frame)
+
+    @property
+    def nnode(self):
+        return self.x.shape[0]
+
+    @property
+    def ncell(self):
+        return self.cell_node.shape[0]
+
+    @property
+    def nfct(self):
+        return self.fct_node.shape[0]
+
+    def boundary_facets(self, sides):
+        sides = np.atleast_1d(np.asarray(sides))
+        return self.bfct[np.isin(self.bfct_side, sides)].astype(np.int32)
+
+
+def _csr(keys: np.ndarray, vals: np.ndarray, n: int):
+    """CSR adjacency key -> sorted vals."""
+    order = np.lexsort((vals, keys))
+    counts = np.bincount(keys, minlength=n)
+    off = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(counts, out=off[1:])
+    return off, vals[order].astype(np.int32)
+
+
+def build_topology(x: np.ndarray, cell_node: np.ndarray) -> Mesh:
+    cell_node = np.ascontiguousarray(cell_node, dtype=np.int32)
+    ncell = cell_node.shape[0]
+    nnode = x.shape[0]
+    x3 = np.zeros((nnode, 3))
+    x3[:, : x.shape[1]] = x
+
+    # edges of every cell, local facet f = vertices FACET_VERTS[f]
+    ea = cell_node[:, FACET_VERTS[:, 0]].astype(np.int64)  # [ncell][3]
+    eb = cell_node[:, FACET_VERTS[:, 1]].astype(np.int64)
+    lo, hi = np.minimum(ea, eb), np.maximum(ea, eb)
+    key = lo * nnode + hi
+    ukey, inv = np.unique(key.ravel(), return_inverse=True)
+    nfct = ukey.shape[0]
+    cell_fct = inv.reshape(ncell, 3).astype(np.int32)
+    fct_node = np.stack([ukey // nnode, ukey % nnode], axis=1).astype(np.int32)
+
+    cells_rep = np.repeat(np.arange(ncell, dtype=np.int64), 3)
+    fct_cell_off, fct_cell = _csr(cell_fct.ravel().astype(np.int64), cells_rep, nfct)
+    node_cell_off, node_cell = _csr(cell_node.ravel().astype(np.int64), cells_rep, nnode)
+    fn = fct_node.ravel().astype(np.int64)
+    node_fct_off, node_fct = _csr(fn, np.repeat(np.arange(nfct, dtype=np.int64), 2), nnode)
+
+    perms = (ea > eb).astype(np.uint8)  # [ncell][3]
+    info = (perms[:, 0].astype(np.uint32) | (perms[:, 1].astype(np.uint32) << 1) | (perms[:, 2].astype(np.uint32) << 2))
+
+    nc_per_f = np.diff(fct_cell_off)
+    bfct = np.nonzero(nc_per_f == 1)[0].astype(np.int32)
+    mid = 0.5 * (x3[fct_node[bfct, 0]] + x3[fct_node[bfct, 1]])
+    side = np.zeros(bfct.shape[0], dtype=np.int32)
+    side[np.isclose(mid[:, 0], 0.0)] = 1
+    side[np.isclose(mid[:, 1], 0.0)] = 2
+    side[np.isclose(mid[:, 0], 1.0)] = 3
+    side[np.isclose(mid[:, 1], 1.0)] = 4
+
+    return Mesh(
+        x=x3,
+        cell_node=cell_node,
+        cell_fct=cell_fct,
+        fct_node=fct_node,
+        fct_cell_off=fct_cell_off,
+        fct_cell=fct_cell,
+        node_cell_off=node_cell_off,
+        node_cell=node_cell,
+        node_fct_off=node_fct_off,
+        node_fct=node_fct,
+        fct_perms=np.ascontiguousarray(perms.ravel()),
+        cell_perm_info=info,
+        bfct=bfct,
+        bfct_side=side,
+    )
+
+
+def _scramble(cell_node, rng):
+    """Random permutation of the local vertex order of every cell: produces
+    reversed facets and negative Jacobians (stand-in for the reference's gmsh
+    fixture `python/test/unit/utils.py:98-137`)."""
+    perm = np.argsort(rng.random(cell_node.shape), axis=1)
+    return np.take_along_axis(cell_node, perm, axis=1)
+
+
+def crossed_unit_square(n: int, scramble_seed: int | None = None, perturb: float = 0.0, seed: int = 7) -> Mesh:
+    """n x n squares, each split into 4 triangles by both diagonals
+    (`DiagonalType.crossed`, the reference's benchmark mesh `perftest.py:62-63`).
+
+    Node ids: grid node (i, j) -> j (n+1) + i, then square centres
+    (n+1)^2 + j n + i.  Cell 4 (j n + i) + t, t = bottom, right, top, left; local
+    vertices ascending in global id."""
+    i, j = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="xy")
+    xg = np.stack([i.ravel() / n, j.ravel() / n], axis=1)
+    ic, jc = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    xc = np.stack([(ic.ravel() + 0.5) / n, (jc.ravel() + 0.5) / n], axis=1)
+    x = np.concatenate([xg, xc])
+    if perturb > 0.0:
+        rng = np.random.default_rng(seed)
+        interior = np.ones(x.shape[0], dtype=bool)
+        interior[: (n + 1) ** 2] = ((i.ravel() > 0) & (i.ravel() < n) & (j.ravel() > 0) & (j.ravel() < n))
+        x[interior] += perturb / n * (rng.random((interior.sum(), 2)) - 0.5)
+
+    sq_i, sq_j = ic.ravel(), jc.ravel()
+    v00 = sq_j * (n + 1) + sq_i
+    v10 = v00 + 1
+    v01 = v00 + (n + 1)
+    v11 = v01 + 1
+    c = (n + 1) ** 2 + sq_j * n + sq_i
+    tris = np.stack(
+        [
+            np.stack([v00, v10, c], axis=1),
+            np.stack([v10, v11, c], axis=1),
+            np.stack([v01, v11, c], axis=1),
+            np.stack([v00, v01, c], axis=1),
+        ],
+        axis=1,
+    ).reshape(-1, 3)
+    if scramble_seed is not None:
+        tris = _scramble(tris, np.random.default_rng(scramble_seed))
+    return build_topology(x, tris)
+
+
+def random_diagonal_square(n: int, seed: int = 3, scramble_seed: int | None = None, perturb: float = 0.0) -> Mesh:
+    """n x n squares split by one randomly chosen diagonal: vertex valences 2..8,
+    i.e. patches with every cell count the reference accepts.  Corner squares get
+    the diagonal that gives the corner node two cells (a 1-cell patch throws in
+    the reference, `se/Patch.cpp:353-359`)."""
+    rng = np.random.default_rng(seed)
+    i, j = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="xy")
+    x = np.stack([i.ravel() / n, j.ravel() / n], axis=1)
+    if perturb > 0.0:
+        interior = (i.ravel() > 0) & (i.ravel() < n) & (j.ravel() > 0) & (j.ravel() < n)
+        x[interior] += perturb / n * (rng.random((interior.sum(), 2)) - 0.5)
+    ic, jc = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    sq_i, sq_j = ic.ravel(), jc.ravel()
+    v00 = sq_j * (n + 1) + sq_i
+    v10, v01 = v00 + 1, v00 + (n + 1)
+    v11 = v01 + 1
+    # diag 0: v00-v11 ("right"), diag 1: v10-v01 ("left")
+    diag = rng.integers(0, 2, size=n * n)
+    diag[(sq_i == 0) & (sq_j == 0)] = 0
+    diag[(sq_i == n - 1) & (sq_j == n - 1)] = 0
+    diag[(sq_i == n - 1) & (sq_j == 0)] = 1
+    diag[(sq_i == 0) & (sq_j == n - 1)] = 1
+    t0 = np.where(diag[:, None] == 0, np.stack([v00, v10, v11], 1), np.stack([v00, v10, v01], 1))
+    t1 = np.where(diag[:, None] == 0, np.stack([v00, v01, v11], 1), np.stack([v10, v01, v11], 1))
+    tris = np.stack([t0, t1], axis=1).reshape(-1, 3)
+    tris = np.sort(tris, axis=1)
+    if scramble_seed is not None:
+        tris = _scramble(tris, np.random.default_rng(scramble_seed))
+    return build_topology(x, tris)
+
+
+def dg_dofmap(ncell: int, ndg: int) -> np.ndarray:
+    """Cell dofmap of a DG_p space: dof = cell * ndg + local (DOLFINx layout)."""
+    return (np.arange(ncell, dtype=np.int32)[:, None] * ndg + np.arange(ndg, dtype=np.int32)[None, :]).astype(np.int32)
+
+
+def facet_types(mesh: Mesh, dirichlet_sides, neumann_sides) -> np.ndarray:
+    """`facet_type[nfct]` int8 with the wire values of `base/Patch.hpp:27-33`:
+    0 internal, 1 essnt_primal (Dirichlet of the primal problem), 2 essnt_dual
+    (flux / Neumann BC)."""
+    ft = np.zeros(mesh.nfct, dtype=np.int8)
+    ft[mesh.boundary_facets(dirichlet_sides)] = 1
+    if len(np.atleast_1d(neumann_sides)):
+        ft[mesh.boundary_facets(neumann_sides)] = 2
+    return ft

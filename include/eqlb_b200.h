@@ -1,0 +1,155 @@
+/* eqlb_b200.h - C ABI of the B200-native flux-equilibration hot path.
+ *
+ * Drop-in boundary: these entry points are what the successor of the reference's
+ * pybind11 module (`python/dolfinx_eqlb/wrappers.cpp`, module `dolfinx_eqlb.cpp`)
+ * binds.  The pybind layer extracts plain arrays from the DOLFINx objects it is
+ * handed and calls into this library; nothing above it changes.
+ *
+ *   reference entry point (wrappers.cpp)                    replaced by
+ *   ------------------------------------------------------  -----------------------
+ *   reconstruct_fluxes_semiexplt             :97-115        eqlb_se_run
+ *   reconstruct_fluxes_semiexplt_with_kornconst :117-137    eqlb_se_run (korn != NULL)
+ *   reconstruct_fluxes_minimisation          :85-95         eqlb_ev_run
+ *   local_solver_cholesky / _lu / _cg        :54-79         eqlb_local_project
+ *   BoundaryData (the part the hot path reads) :235-256     eqlb_set_bcs
+ *
+ * All functions return 0 on success; on failure a negative code, with the text
+ * of the `std::runtime_error` the reference would have thrown available from
+ * eqlb_last_error().  Buffers are caller-owned; `memspace` says whether data
+ * pointers are host (EQLB_HOST) or device (EQLB_DEVICE) memory.  There is no
+ * CPU fallback: every compute entry point runs CUDA kernels and fails with
+ * EQLB_ERR_CUDA if no device is usable.
+ */
+#ifndef EQLB_B200_H
+#define EQLB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQLB_HOST 0
+#define EQLB_DEVICE 1
+
+#define EQLB_OK 0
+#define EQLB_ERR_INPUT (-1)   /* the reference's std::runtime_error on bad input */
+#define EQLB_ERR_CUDA (-2)    /* CUDA runtime / no device */
+#define EQLB_ERR_STATE (-3)   /* call order (e.g. run before set_bcs) */
+
+/* flags for eqlb_create */
+#define EQLB_FLAG_STRESS 1u   /* first gdim fluxes are rows of a stress tensor (weak symmetry) */
+#define EQLB_FLAG_ATOMIC 2u   /* accumulate with fp64 atomics instead of colour-ordered launches */
+
+/* wire values, `base/Patch.hpp:20-33` */
+enum eqlb_patch_type { EQLB_PATCH_INTERNAL = 0, EQLB_PATCH_ESSNT_DUAL = 1,
+                       EQLB_PATCH_ESSNT_PRIMAL = 2, EQLB_PATCH_MIXED = 3 };
+enum eqlb_facet_type { EQLB_FCT_INTERNAL = 0, EQLB_FCT_ESSNT_PRIMAL = 1,
+                       EQLB_FCT_ESSNT_DUAL = 2 };
+
+/* Mesh arrays: exactly the DOLFINx accessors the reference reads
+ * (`se/Patch.cpp:23-28`, `se/reconstruction.hpp:83-93`,
+ *  `se/solve_patch_semiexplt.hpp:223-224,454-463`, `ev/reconstruction.hpp:79-107`).
+ * Always HOST pointers (read once at eqlb_create and copied to the device). */
+typedef struct eqlb_mesh {
+  int32_t nnode, ncell, nfct;
+  const double*   x;              /* [nnode*3]  geometry().x()                       */
+  const int32_t*  cell_node;      /* [ncell*3]  geometry().dofmap() == connectivity(2,0) */
+  const int32_t*  cell_fct;       /* [ncell*3]  connectivity(2,1)                    */
+  const int32_t*  fct_node;       /* [nfct*2]   connectivity(1,0)                    */
+  const int32_t*  fct_cell_off;   /* [nfct+1]   connectivity(1,2) offsets            */
+  const int32_t*  fct_cell;       /*            connectivity(1,2) array              */
+  const int32_t*  node_cell_off;  /* [nnode+1]  connectivity(0,2)                    */
+  const int32_t*  node_cell;
+  const int32_t*  node_fct_off;   /* [nnode+1]  connectivity(0,1)                    */
+  const int32_t*  node_fct;
+  const uint8_t*  fct_perms;      /* [ncell*3]  topology().get_facet_permutations()  */
+  const uint32_t* cell_perm_info; /* [ncell]    topology().get_cell_permutation_info() */
+  const int32_t*  dg_dofmap;      /* [ncell*ndg] dofmap of the DG_p space of G and f */
+} eqlb_mesh;
+
+/* Reference-element tables (dolfinx_eqlb_b200/tables.py; Basix-derived in a
+ * DOLFINx deployment).  HOST pointers. Shapes in tables.py::Tables. */
+typedef struct eqlb_tables {
+  int32_t k, p, nrt, ndg, ndg_fct, nq, nqf, ndiv, nadd;
+  /* quadrature-style tables (what se::KernelData holds) */
+  const double *qpts, *qwts, *fpts_s, *fwts, *M, *rt_q, *rt_f, *dg_q, *dg_f, *hat_q, *hat_f, *trafo;
+  const int32_t *fct_closure, *div_lm;
+  /* reference-matrix tables (exact integrals on the reference cell) */
+  const double *rt_mass, *fct_mom, *cell_mom_f, *cell_mom_g, *bc_mat, *rt_p1;
+} eqlb_tables;
+
+typedef struct eqlb_handle eqlb_handle;
+
+/* Build the device-resident problem: copies mesh + tables to the GPU.
+ * Replaces the one-time part of `se::reconstruction` (`se/reconstruction.hpp:62-153`)
+ * and `ev::reconstruction` (`ev/reconstruction.hpp:64-127`).
+ * Errors like the reference: 1-cell patches (`se/Patch.cpp:353-359`), bad degrees
+ * (`se/reconstruction.hpp:358-388`). */
+int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* tables, int nrhs,
+                uint32_t flags, eqlb_handle** out);
+void eqlb_destroy(eqlb_handle* h);
+
+/* CUDA stream all later launches go to (a cudaStream_t; NULL = default stream). */
+int eqlb_set_stream(eqlb_handle* h, void* cuda_stream);
+
+/* Boundary data consumed by the hot path = the state of `base::BoundaryData`
+ * after its constructor (`base/BoundaryData.cpp:279-633`):
+ *   facet_type  [nrhs*nfct] int8  (eqlb_facet_type)
+ *   bflux[i]    [ncell*nrt] f64   boundary function of rhs i (DRT layout), may be
+ *                                 NULL when rhs i has no flux BC
+ *   local_fct_id[nfct]      int8  cell-local id of each flux-BC facet
+ *   node_on_stress_bnd [nnode] int8 (stress only, else NULL)
+ * Runs the device patch builder (integer maps, patch types, colouring).
+ * HOST pointers. */
+int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* bflux,
+                 const int8_t* local_fct_id, const int8_t* node_on_stress_bnd);
+
+/* Semi-explicit equilibration: sigma[i] += equilibrated corrector of rhs i.
+ *   G[i]     [ncell*ndg*2] projected flux (blocked bs=2), f[i] [ncell*ndg] projected RHS
+ *   sigma[i] [ncell*nrt]   DRT_k vector, ACCUMULATED like the reference
+ *                          (`se/solve_patch_semiexplt.hpp:1159`)
+ *   korn     [ncell] or NULL: += 3 * squared Korn constants (`se/reconstruction.hpp:248-260`) */
+int eqlb_se_run(eqlb_handle* h, const double* const* G, const double* const* f,
+                double* const* sigma, double* korn, int memspace);
+
+/* Constrained-minimisation (Ern-Vohralik) equilibration on the mixed RT_k x DG_(k-1)
+ * patch spaces; sigma[i] [nfct*k + ncell*(k*k-k)] conforming hierarchic-RT vector,
+ * ACCUMULATED (`ev/solve_patch.hpp:216-227`). */
+int eqlb_ev_run(eqlb_handle* h, const double* const* G, const double* const* f,
+                double* const* sigma, int memspace);
+
+/* Cell-wise L2 projection into DG_p (the fixed-form fast path of
+ * `base::local_solver_cholesky`, `base/local_solver.hpp:38-187`, as used by
+ * `lsolver/projection.py:17-77`): out[cell*ndg+i] = dofs of the projection of the
+ * function given by its values at the nq cell quadrature points.
+ *   qvals [nfun][ncell*nq], out [nfun][ncell*ndg] (assigned, not accumulated). */
+int eqlb_local_project(eqlb_handle* h, int nfun, const double* const* qvals,
+                       double* const* out, int memspace);
+
+/* Integer patch maps in the reference's layout, for bit-exact comparison
+ * (SURVEY App. A).  All HOST output buffers, padded with -1 beyond a patch's
+ * size; ncmax from eqlb_patch_dims.  Any pointer may be NULL.
+ *   ncells[npatch], cells/fcts/inodes_local [npatch*(ncmax+2)],
+ *   fcts_local [npatch*2*(ncmax+1)], type [npatch*nrhs],
+ *   reversed [npatch*ncmax*2], reversion [npatch*nrhs], colour[npatch] */
+int eqlb_patch_dims(eqlb_handle* h, int32_t* npatch, int32_t* ncmax, int32_t* ncolours);
+int eqlb_get_patch_maps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t* fcts,
+                        int8_t* inodes_local, int8_t* fcts_local, int8_t* type,
+                        uint8_t* reversed, uint8_t* reversion, int32_t* colour);
+/* SE 4-plane DOF map + facet DOFs of the projected flux + boundary markers:
+ *   dofmap [npatch*4*(ncmax+2)*ndpc], ndpc = 2k+nadd(+3 if stress)+ndiv
+ *   projflux_fct [npatch*(ncmax+1)*2*ndg_fct], bmarkers [npatch*nrhs*hzmax] */
+int eqlb_get_se_dofmaps(eqlb_handle* h, int32_t* dofmap, int32_t* projflux_fct,
+                        int8_t* bmarkers, int32_t* ndpc, int32_t* hzmax);
+
+/* number of kernel launches issued by this handle so far (bench "gpu_launches") */
+int64_t eqlb_launch_count(eqlb_handle* h);
+
+const char* eqlb_last_error(void);
+const char* eqlb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQLB_B200_H */

@@ -1,0 +1,565 @@
+// Host side of the C ABI (include/eqlb_b200.h): validation, device residency of
+// mesh / tables / boundary data, patch colouring, staging of host buffers.
+// Mirrors the drivers se/reconstruction.hpp:337-407 and ev/reconstruction.hpp:157-177
+// (input checks and error texts), everything numerical runs in CUDA kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "eqlb_internal.cuh"
+
+static thread_local std::string g_last_error;
+void eqlb_set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace
+{
+
+template <typename F>
+int guarded(F&& f)
+{
+  try
+  {
+    f();
+    return EQLB_OK;
+  }
+  catch (const EqlbError& e)
+  {
+    g_last_error = e.what();
+    return e.code;
+  }
+  catch (const std::exception& e)
+  {
+    g_last_error = e.what();
+    return EQLB_ERR_INPUT;
+  }
+}
+
+void require_device()
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw EqlbError(EQLB_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ")
+                                       + cudaGetErrorString(e));
+}
+
+// Greedy vertex colouring such that two patches of one colour never share a cell
+// (two vertices of a common cell get different colours).  Deterministic: vertices
+// in ascending order, smallest free colour.
+void colour_patches(eqlb_handle* h)
+{
+  const int n = h->nnode;
+  h->h_colour.assign(n, -1);
+  int ncol = 0;
+  for (int z = 0; z < n; ++z)
+  {
+    uint64_t used = 0;
+    for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
+    {
+      const int32_t* cn = &h->h_cell_node[3 * (size_t)h->h_node_cell[i]];
+      for (int j = 0; j < 3; ++j)
+      {
+        const int c = h->h_colour[cn[j]];
+        if (c >= 0)
+          used |= (uint64_t(1) << c);
+      }
+    }
+    int c = 0;
+    while (used & (uint64_t(1) << c))
+      ++c;
+    h->h_colour[z] = c;
+    ncol = std::max(ncol, c + 1);
+  }
+  h->ncolours = ncol;
+  h->h_colour_off.assign(ncol + 1, 0);
+  for (int z = 0; z < n; ++z)
+    h->h_colour_off[h->h_colour[z] + 1]++;
+  for (int c = 0; c < ncol; ++c)
+    h->h_colour_off[c + 1] += h->h_colour_off[c];
+  std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
+  h->h_order.resize(n);
+  for (int z = 0; z < n; ++z)
+    h->h_order[pos[h->h_colour[z]]++] = z;
+}
+
+void append(std::vector<double>& dst, const double* src, size_t n, int& offset)
+{
+  offset = (int)dst.size();
+  dst.insert(dst.end(), src, src + n);
+  while (dst.size() % 2)
+    dst.push_back(0.0);
+}
+
+} // namespace
+
+extern "C"
+{
+
+const char* eqlb_last_error(void) { return g_last_error.c_str(); }
+const char* eqlb_version(void) { return "eqlb_b200 0.1 (sm_100a)"; }
+
+int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t flags, eqlb_handle** out)
+{
+  return guarded(
+      [&]
+      {
+        if (!mesh || !t || !out)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_create: null argument");
+        *out = nullptr;
+        // input checks of se/reconstruction.hpp:358-388
+        if (nrhs < 1 || nrhs > EQLB_MAXRHS)
+          throw EqlbError(EQLB_ERR_INPUT, "Equilibration: Input sizes does not match");
+        if (t->p > t->k - 1)
+          throw EqlbError(EQLB_ERR_INPUT, "Equilibration: Wrong polynomial degree of the projected RHS");
+        if ((flags & EQLB_FLAG_STRESS) && nrhs < 2)
+          throw EqlbError(EQLB_ERR_INPUT, "Stress equilibration: Specify all rows of stress tensor");
+        if ((flags & EQLB_FLAG_STRESS) && t->k < 2)
+          throw EqlbError(EQLB_ERR_INPUT, "Stress equilibration: RT_k with k>1 required!");
+        // patch sizes (se/Patch.cpp:337-404)
+        int ncmax = 0;
+        for (int i = 0; i < mesh->nnode; ++i)
+        {
+          const int nc = mesh->node_cell_off[i + 1] - mesh->node_cell_off[i];
+          if (nc == 1)
+            throw EqlbError(EQLB_ERR_INPUT,
+                            "Patch around node " + std::to_string(i) + " has only 1 cells.");
+          ncmax = std::max(ncmax, nc);
+        }
+        if (ncmax > EQLB_NCMAX)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_b200: patches with more than " + std::to_string(EQLB_NCMAX)
+                                              + " cells are not supported");
+        require_device();
+
+        std::unique_ptr<eqlb_handle> h(new eqlb_handle());
+        CUDA_CHECK(cudaGetDevice(&h->device));
+        h->flags = flags;
+        h->nrhs = nrhs;
+        h->nnode = mesh->nnode;
+        h->ncell = mesh->ncell;
+        h->nfct = mesh->nfct;
+        h->k = t->k;
+        h->p = t->p;
+        h->nrt = t->nrt;
+        h->ndg = t->ndg;
+        h->ndg_fct = t->ndg_fct;
+        h->ndiv = t->ndiv;
+        h->nadd = t->nadd;
+        h->nq = t->nq;
+        h->nqf = t->nqf;
+        h->ncmax = ncmax;
+
+        const size_t nn = mesh->nnode, nc = mesh->ncell, nf = mesh->nfct;
+        h->d_x.upload(mesh->x, nn * 3);
+        h->d_cell_node.upload(mesh->cell_node, nc * 3);
+        h->d_cell_fct.upload(mesh->cell_fct, nc * 3);
+        h->d_fct_node.upload(mesh->fct_node, nf * 2);
+        h->d_fct_cell_off.upload(mesh->fct_cell_off, nf + 1);
+        h->d_fct_cell.upload(mesh->fct_cell, mesh->fct_cell_off[nf]);
+        h->d_node_cell_off.upload(mesh->node_cell_off, nn + 1);
+        h->d_node_cell.upload(mesh->node_cell, mesh->node_cell_off[nn]);
+        h->d_node_fct_off.upload(mesh->node_fct_off, nn + 1);
+        h->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
+        h->d_fct_perms.upload(mesh->fct_perms, nc * 3);
+        h->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
+        h->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
+        h->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
+
+        // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
+        h->dg_identity = true;
+        if (mesh->dg_dofmap)
+        {
+          for (size_t i = 0; i < nc * (size_t)t->ndg; ++i)
+            if (mesh->dg_dofmap[i] != (int32_t)i)
+            {
+              h->dg_identity = false;
+              break;
+            }
+          if (!h->dg_identity)
+            h->d_dg_dofmap.upload(mesh->dg_dofmap, nc * t->ndg);
+        }
+
+        // reference-matrix tables -> one flat device block
+        std::vector<double> flat;
+        TableView& tv = h->tv;
+        tv.k = t->k;
+        tv.p = t->p;
+        tv.nrt = t->nrt;
+        tv.ndg = t->ndg;
+        tv.ndg_fct = t->ndg_fct;
+        tv.ndiv = t->ndiv;
+        tv.nadd = t->nadd;
+        const int k = t->k, nrt = t->nrt, ndg = t->ndg, nt = 1 + t->ndiv;
+        append(flat, t->rt_mass, (size_t)3 * nrt * nrt, tv.o_rt_mass);
+        append(flat, t->fct_mom, (size_t)9 * k * ndg, tv.o_fct_mom);
+        append(flat, t->cell_mom_f, (size_t)3 * nt * ndg, tv.o_cell_mom_f);
+        append(flat, t->cell_mom_g, (size_t)3 * nt * ndg * 2, tv.o_cell_mom_g);
+        append(flat, t->bc_mat, (size_t)9 * k * k, tv.o_bc_mat);
+        append(flat, t->trafo, (size_t)k * k, tv.o_trafo);
+        append(flat, t->rt_p1, (size_t)nrt * 6, tv.o_rt_p1);
+        h->d_tables.upload(flat.data(), flat.size());
+        tv.data = h->d_tables.p;
+        tv.ndoubles = (int)flat.size();
+
+        // cell-wise L2 projector into DG_p: P = M^-1 Phi^T W  (ndg x nq), reference cell
+        {
+          const int nq = t->nq;
+          std::vector<double> Mm((size_t)ndg * ndg, 0.0), P((size_t)ndg * nq, 0.0);
+          for (int q = 0; q < nq; ++q)
+            for (int i = 0; i < ndg; ++i)
+              for (int j = 0; j < ndg; ++j)
+                Mm[i * ndg + j] += t->qwts[q] * t->dg_q[(size_t)q * ndg + i] * t->dg_q[(size_t)q * ndg + j];
+          // Cholesky of the reference mass matrix
+          std::vector<double> Lc(Mm);
+          for (int j = 0; j < ndg; ++j)
+          {
+            double d = Lc[j * ndg + j];
+            for (int q = 0; q < j; ++q)
+              d -= Lc[j * ndg + q] * Lc[j * ndg + q];
+            d = std::sqrt(d);
+            Lc[j * ndg + j] = d;
+            for (int i = j + 1; i < ndg; ++i)
+            {
+              double s = Lc[i * ndg + j];
+              for (int q = 0; q < j; ++q)
+                s -= Lc[i * ndg + q] * Lc[j * ndg + q];
+              Lc[i * ndg + j] = s / d;
+            }
+          }
+          for (int q = 0; q < nq; ++q)
+          {
+            std::vector<double> b(ndg);
+            for (int i = 0; i < ndg; ++i)
+              b[i] = t->qwts[q] * t->dg_q[(size_t)q * ndg + i];
+            for (int i = 0; i < ndg; ++i)
+            {
+              double s = b[i];
+              for (int c = 0; c < i; ++c)
+                s -= Lc[i * ndg + c] * b[c];
+              b[i] = s / Lc[i * ndg + i];
+            }
+            for (int i = ndg - 1; i >= 0; --i)
+            {
+              double s = b[i];
+              for (int c = i + 1; c < ndg; ++c)
+                s -= Lc[c * ndg + i] * b[c];
+              b[i] = s / Lc[i * ndg + i];
+            }
+            for (int i = 0; i < ndg; ++i)
+              P[(size_t)i * nq + q] = b[i];
+          }
+          h->d_proj.upload(P.data(), P.size());
+        }
+
+        launch_compute_cellJ(h.get());
+        colour_patches(h.get());
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        *out = h.release();
+      });
+}
+
+void eqlb_destroy(eqlb_handle* h) { delete h; }
+
+int eqlb_set_stream(eqlb_handle* h, void* cuda_stream)
+{
+  return guarded(
+      [&]
+      {
+        if (!h)
+          throw EqlbError(EQLB_ERR_INPUT, "null handle");
+        h->stream = (cudaStream_t)cuda_stream;
+      });
+}
+
+int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* bflux, const int8_t* local_fct_id,
+                 const int8_t* node_on_stress_bnd)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !facet_type)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs: null argument");
+        (void)local_fct_id;  // implied by the patch maps (local id of the boundary facet in its only cell)
+        const size_t nf = h->nfct;
+        // every boundary facet has to be classified for every RHS (se/Patch.cpp:464-470)
+        h->d_facet_type.upload(facet_type, (size_t)h->nrhs * nf);
+        const size_t nb = (size_t)h->ncell * h->nrt;
+        h->d_bflux.alloc((size_t)h->nrhs * nb);
+        h->d_bflux.zero(h->stream);
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < h->nrhs; ++r)
+          if (bflux && bflux[r])
+            CUDA_CHECK(cudaMemcpy(h->d_bflux.p + (size_t)r * nb, bflux[r], nb * sizeof(double), cudaMemcpyHostToDevice));
+        if (node_on_stress_bnd)
+          h->d_node_on_bnd.upload(node_on_stress_bnd, h->nnode);
+
+        // patch records (colour-sorted)
+        h->pstride = ((size_t)h->nnode + 31) / 32 * 32;
+        h->d_pnode.alloc(h->pstride);
+        h->d_pncells.alloc(h->pstride);
+        h->d_pcell.alloc(h->pstride * h->ncmax);
+        h->d_pinfo.alloc(h->pstride * h->ncmax);
+        h->d_prhs.alloc(h->pstride * h->nrhs);
+        h->d_pcell.zero(h->stream);
+        h->d_pinfo.zero(h->stream);
+        launch_patch_builder(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        h->bcs_set = true;
+      });
+}
+
+int eqlb_patch_dims(eqlb_handle* h, int32_t* npatch, int32_t* ncmax, int32_t* ncolours)
+{
+  return guarded(
+      [&]
+      {
+        if (!h)
+          throw EqlbError(EQLB_ERR_INPUT, "null handle");
+        if (npatch)
+          *npatch = h->nnode;
+        if (ncmax)
+          *ncmax = h->ncmax;
+        if (ncolours)
+          *ncolours = h->ncolours;
+      });
+}
+
+int eqlb_get_patch_maps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t* fcts, int8_t* inodes_local,
+                        int8_t* fcts_local, int8_t* type, uint8_t* reversed, uint8_t* reversion, int32_t* colour)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_get_patch_maps: call eqlb_set_bcs first");
+        const size_t np = h->nnode, w = h->ncmax + 2;
+        DevBuf<int32_t> d_nc, d_cells, d_fcts;
+        DevBuf<int8_t> d_inod, d_fl, d_type;
+        DevBuf<uint8_t> d_rev, d_reversion;
+        d_nc.alloc(np);
+        d_cells.alloc(np * w);
+        d_fcts.alloc(np * w);
+        d_inod.alloc(np * w);
+        d_fl.alloc(np * 2 * (h->ncmax + 1));
+        d_type.alloc(np * h->nrhs);
+        d_rev.alloc(np * h->ncmax * 2);
+        d_reversion.alloc(np * h->nrhs);
+        CUDA_CHECK(cudaMemsetAsync(d_cells.p, 0xFF, np * w * 4, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(d_fcts.p, 0xFF, np * w * 4, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(d_inod.p, 0xFF, np * w, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(d_fl.p, 0xFF, np * 2 * (h->ncmax + 1), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(d_rev.p, 0xFF, np * h->ncmax * 2, h->stream));
+        launch_patch_builder(h, d_nc.p, d_cells.p, d_fcts.p, d_inod.p, d_fl.p, d_type.p, d_rev.p, d_reversion.p);
+        auto fetch = [&](void* dst, const void* src, size_t bytes)
+        {
+          if (dst)
+            CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+        };
+        fetch(ncells, d_nc.p, np * 4);
+        fetch(cells, d_cells.p, np * w * 4);
+        fetch(fcts, d_fcts.p, np * w * 4);
+        fetch(inodes_local, d_inod.p, np * w);
+        fetch(fcts_local, d_fl.p, np * 2 * (h->ncmax + 1));
+        fetch(type, d_type.p, np * h->nrhs);
+        fetch(reversed, d_rev.p, np * h->ncmax * 2);
+        fetch(reversion, d_reversion.p, np * h->nrhs);
+        if (colour)
+          std::memcpy(colour, h->h_colour.data(), np * 4);
+      });
+}
+
+int eqlb_get_se_dofmaps(eqlb_handle* h, int32_t* dofmap, int32_t* projflux_fct, int8_t* bmarkers, int32_t* ndpc_out,
+                        int32_t* hzmax_out)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_get_se_dofmaps: call eqlb_set_bcs first");
+        const bool stress = (h->flags & EQLB_FLAG_STRESS) != 0;
+        const int ndpc = 2 * h->k + h->nadd + h->ndiv + (stress ? 3 : 0);
+        const int hzmax = 1 + (h->k - 1) * (h->ncmax + 1) + h->nadd * h->ncmax;
+        if (ndpc_out)
+          *ndpc_out = ndpc;
+        if (hzmax_out)
+          *hzmax_out = hzmax;
+        const size_t np = h->nnode;
+        DevBuf<int32_t> d_dm, d_pf;
+        DevBuf<int8_t> d_bm;
+        const size_t n_dm = np * 4 * (h->ncmax + 2) * ndpc, n_pf = np * (h->ncmax + 1) * 2 * h->ndg_fct,
+                     n_bm = np * h->nrhs * hzmax;
+        if (dofmap)
+        {
+          d_dm.alloc(n_dm);
+          CUDA_CHECK(cudaMemsetAsync(d_dm.p, 0xFF, n_dm * 4, h->stream));
+        }
+        if (projflux_fct)
+        {
+          d_pf.alloc(n_pf);
+          CUDA_CHECK(cudaMemsetAsync(d_pf.p, 0xFF, n_pf * 4, h->stream));
+        }
+        if (bmarkers)
+        {
+          d_bm.alloc(n_bm);
+          CUDA_CHECK(cudaMemsetAsync(d_bm.p, 0xFF, n_bm, h->stream));
+        }
+        launch_se_dofmaps(h, d_dm.p, d_pf.p, d_bm.p, ndpc, hzmax);
+        if (dofmap)
+          CUDA_CHECK(cudaMemcpy(dofmap, d_dm.p, n_dm * 4, cudaMemcpyDeviceToHost));
+        if (projflux_fct)
+          CUDA_CHECK(cudaMemcpy(projflux_fct, d_pf.p, n_pf * 4, cudaMemcpyDeviceToHost));
+        if (bmarkers)
+          CUDA_CHECK(cudaMemcpy(bmarkers, d_bm.p, n_bm, cudaMemcpyDeviceToHost));
+      });
+}
+
+int eqlb_se_run(eqlb_handle* h, const double* const* G, const double* const* f, double* const* sigma, double* korn,
+                int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !G || !f || !sigma)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_se_run: null argument");
+        if (!h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_se_run: call eqlb_set_bcs first");
+        const int nrhs = h->nrhs;
+        const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg,
+                     nS = (size_t)h->ncell * h->nrt;
+        const double* dG[EQLB_MAXRHS];
+        const double* dF[EQLB_MAXRHS];
+        double* dS[EQLB_MAXRHS];
+        double* dK = korn;
+        if (memspace == EQLB_DEVICE)
+        {
+          for (int r = 0; r < nrhs; ++r)
+          {
+            dG[r] = G[r];
+            dF[r] = f[r];
+            dS[r] = sigma[r];
+          }
+        }
+        else
+        {
+          h->d_stage_G.alloc(nG * nrhs);
+          h->d_stage_f.alloc(nF * nrhs);
+          h->d_stage_sigma.alloc(nS * nrhs);
+          for (int r = 0; r < nrhs; ++r)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_G.p + r * nG, G[r], nG * 8, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_f.p + r * nF, f[r], nF * 8, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_sigma.p + r * nS, sigma[r], nS * 8, cudaMemcpyHostToDevice, h->stream));
+            dG[r] = h->d_stage_G.p + r * nG;
+            dF[r] = h->d_stage_f.p + r * nF;
+            dS[r] = h->d_stage_sigma.p + r * nS;
+          }
+          if (korn)
+          {
+            h->d_stage_korn.alloc(h->ncell);
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_korn.p, korn, (size_t)h->ncell * 8, cudaMemcpyHostToDevice, h->stream));
+            dK = h->d_stage_korn.p;
+          }
+        }
+        launch_se(h, dG, dF, dS, dK);
+        if (memspace != EQLB_DEVICE)
+        {
+          for (int r = 0; r < nrhs; ++r)
+            CUDA_CHECK(cudaMemcpyAsync(sigma[r], dS[r], nS * 8, cudaMemcpyDeviceToHost, h->stream));
+          if (korn)
+            CUDA_CHECK(cudaMemcpyAsync(korn, dK, (size_t)h->ncell * 8, cudaMemcpyDeviceToHost, h->stream));
+          CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+      });
+}
+
+int eqlb_ev_run(eqlb_handle* h, const double* const* G, const double* const* f, double* const* sigma, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !G || !f || !sigma)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_ev_run: null argument");
+        if (!h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_ev_run: call eqlb_set_bcs first");
+        const int nrhs = h->nrhs;
+        const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg,
+                     nS = (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k);
+        const double* dG[EQLB_MAXRHS];
+        const double* dF[EQLB_MAXRHS];
+        double* dS[EQLB_MAXRHS];
+        if (memspace == EQLB_DEVICE)
+        {
+          for (int r = 0; r < nrhs; ++r)
+          {
+            dG[r] = G[r];
+            dF[r] = f[r];
+            dS[r] = sigma[r];
+          }
+        }
+        else
+        {
+          h->d_stage_G.alloc(nG * nrhs);
+          h->d_stage_f.alloc(nF * nrhs);
+          h->d_stage_sigma.alloc(nS * nrhs);
+          for (int r = 0; r < nrhs; ++r)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_G.p + r * nG, G[r], nG * 8, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_f.p + r * nF, f[r], nF * 8, cudaMemcpyHostToDevice, h->stream));
+            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_sigma.p + r * nS, sigma[r], nS * 8, cudaMemcpyHostToDevice, h->stream));
+            dG[r] = h->d_stage_G.p + r * nG;
+            dF[r] = h->d_stage_f.p + r * nF;
+            dS[r] = h->d_stage_sigma.p + r * nS;
+          }
+        }
+        launch_ev(h, dG, dF, dS);
+        if (memspace != EQLB_DEVICE)
+        {
+          for (int r = 0; r < nrhs; ++r)
+            CUDA_CHECK(cudaMemcpyAsync(sigma[r], dS[r], nS * 8, cudaMemcpyDeviceToHost, h->stream));
+          CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+      });
+}
+
+int eqlb_local_project(eqlb_handle* h, int nfun, const double* const* qvals, double* const* out, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !qvals || !out || nfun < 1)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_local_project: bad argument");
+        const size_t nin = (size_t)h->ncell * h->nq, nout = (size_t)h->ncell * h->ndg;
+        std::vector<const double*> dq(nfun);
+        std::vector<double*> dout(nfun);
+        DevBuf<double> stage_in, stage_out;
+        if (memspace == EQLB_DEVICE)
+        {
+          for (int i = 0; i < nfun; ++i)
+          {
+            dq[i] = qvals[i];
+            dout[i] = out[i];
+          }
+        }
+        else
+        {
+          stage_in.alloc(nin * nfun);
+          stage_out.alloc(nout * nfun);
+          for (int i = 0; i < nfun; ++i)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(stage_in.p + i * nin, qvals[i], nin * 8, cudaMemcpyHostToDevice, h->stream));
+            dq[i] = stage_in.p + i * nin;
+            dout[i] = stage_out.p + i * nout;
+          }
+        }
+        launch_project(h, nfun, dq.data(), dout.data());
+        if (memspace != EQLB_DEVICE)
+        {
+          for (int i = 0; i < nfun; ++i)
+            CUDA_CHECK(cudaMemcpyAsync(out[i], dout[i], nout * 8, cudaMemcpyDeviceToHost, h->stream));
+          CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+      });
+}
+
+int64_t eqlb_launch_count(eqlb_handle* h) { return h ? h->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,195 @@
+// Internal declarations shared by the translation units of libeqlb_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/eqlb_b200.h"
+
+#define EQLB_NCMAX 16  // hard upper bound of cells per patch supported by the kernels
+#define EQLB_MAXRHS 8  // max number of simultaneously equilibrated fluxes
+
+// device pointers of the per-RHS vectors, passed by value as kernel parameter
+struct RhsPtrs
+{
+  const double* G[EQLB_MAXRHS];
+  const double* F[EQLB_MAXRHS];
+  double* S[EQLB_MAXRHS];
+};
+
+// ---------------------------------------------------------------------------
+// error handling: mirror the reference's `throw std::runtime_error` -> status code
+// ---------------------------------------------------------------------------
+struct EqlbError : std::runtime_error
+{
+  int code;
+  EqlbError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                            \
+  do                                                                                                \
+  {                                                                                                 \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw EqlbError(EQLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+void eqlb_set_error(const std::string& msg);
+
+// ---------------------------------------------------------------------------
+// simple owning device buffer
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count)
+  {
+    if (count == n && p)
+      return;
+    release();
+    if (count == 0)
+      return;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* host, size_t count)
+  {
+    alloc(count);
+    if (count)
+      CUDA_CHECK(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void zero(cudaStream_t s = 0)
+  {
+    if (n)
+      CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+// ---------------------------------------------------------------------------
+// device views
+// ---------------------------------------------------------------------------
+
+// Reference-matrix tables in one flat device array (doubles); offsets in doubles.
+// Kernels copy the block into shared memory (a few KB) at CTA start.
+struct TableView
+{
+  const double* data;  // device
+  int ndoubles;
+  int k, p, nrt, ndg, ndg_fct, ndiv, nadd;
+  int o_rt_mass;     // [3][nrt][nrt]
+  int o_fct_mom;     // [3][3][k][ndg]
+  int o_cell_mom_f;  // [3][1+ndiv][ndg]
+  int o_cell_mom_g;  // [3][1+ndiv][ndg][2]
+  int o_bc_mat;      // [3][3][k][k]
+  int o_trafo;       // [k][k]
+  int o_rt_p1;       // [nrt][2][3]
+};
+
+// Mesh connectivity on the device (patch builder input)
+struct MeshView
+{
+  int nnode, ncell, nfct;
+  const double* x;  // [nnode*3]
+  const int32_t *cell_node, *cell_fct, *fct_node, *fct_cell_off, *fct_cell, *node_cell_off, *node_cell, *node_fct_off,
+      *node_fct;
+  const uint8_t* fct_perms;
+};
+
+// Compact patch records, stored in colour-sorted order (position i <-> node order[i]).
+// SoA with the patch index fastest so that a warp of consecutive patches loads
+// coalesced.  info byte per (cell slot a, patch): bits 0-1 local id of the patch
+// node in T_a, bits 2-3 local facet id of E_{a-1} in T_a, bits 4-5 local facet id of
+// E_a in T_a, bit 6 reversed(a,0), bit 7 reversed(a,1).
+// rhs byte per (rhs, patch): bits 0-1 patch type, bit 2 reversion_required,
+// bit 3 E_0 carries a flux BC, bit 4 E_n carries a flux BC.
+struct PatchView
+{
+  int npatch;       // number of patches (== nnode)
+  int ncmax;        // max cells per patch
+  int nrhs;
+  size_t stride;    // padded npatch (multiple of 32)
+  const int32_t* node;   // [stride]     patch-central node
+  const uint8_t* ncells; // [stride]
+  const int32_t* cell;   // [ncmax][stride]
+  const uint8_t* info;   // [ncmax][stride]
+  const uint8_t* rhsinfo; // [nrhs][stride]
+};
+
+struct eqlb_handle
+{
+  int device = 0;
+  cudaStream_t stream = 0;
+  uint32_t flags = 0;
+  int nrhs = 0;
+  bool bcs_set = false;
+  int64_t launches = 0;
+
+  // sizes
+  int nnode = 0, ncell = 0, nfct = 0;
+  int k = 0, p = 0, nrt = 0, ndg = 0, ndg_fct = 0, ndiv = 0, nadd = 0, nq = 0, nqf = 0;
+  int ncmax = 0;
+  bool dg_identity = true;
+
+  // mesh on device
+  DevBuf<double> d_x;
+  DevBuf<int32_t> d_cell_node, d_cell_fct, d_fct_node, d_fct_cell_off, d_fct_cell, d_node_cell_off, d_node_cell,
+      d_node_fct_off, d_node_fct, d_dg_dofmap;
+  DevBuf<uint8_t> d_fct_perms;
+  DevBuf<double> d_cellJ;  // [ncell][4] Jacobians (J00,J01,J10,J11)
+
+  // host copies needed for colouring / validation
+  std::vector<int32_t> h_node_cell_off, h_node_cell, h_cell_node;
+
+  // tables
+  DevBuf<double> d_tables;
+  TableView tv{};
+  std::vector<double> h_tables_q;  // quadrature style tables needed by the projector (dg_q, qwts)
+  DevBuf<double> d_proj;           // [ndg][nq] projection operator (mass^-1 * dg_q^T * w)
+
+  // boundary data
+  DevBuf<int8_t> d_facet_type;  // [nrhs][nfct]
+  DevBuf<double> d_bflux;       // [nrhs][ncell*nrt] (zeros where absent)
+  std::vector<uint8_t> h_has_bflux;
+  DevBuf<int8_t> d_node_on_bnd;
+
+  // patches
+  std::vector<int32_t> h_order;       // colour-sorted node order
+  std::vector<int32_t> h_colour_off;  // [ncolours+1]
+  std::vector<int32_t> h_colour;      // [nnode]
+  int ncolours = 0;
+  size_t pstride = 0;
+  DevBuf<int32_t> d_pnode, d_pcell;
+  DevBuf<uint8_t> d_pncells, d_pinfo, d_prhs;
+
+  // staging buffers for host-pointer calls
+  DevBuf<double> d_stage_G, d_stage_f, d_stage_sigma, d_stage_korn;
+
+  MeshView mesh_view() const;
+  PatchView patch_view() const;
+};
+
+// kernels launchers (defined in the .cu files)
+void launch_compute_cellJ(eqlb_handle* h);
+void launch_patch_builder(eqlb_handle* h, int32_t* d_ncells_out, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inodes,
+                          int8_t* d_fcts_local, int8_t* d_type, uint8_t* d_reversed, uint8_t* d_reversion);
+void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, int8_t* d_bmarkers, int ndpc, int hzmax);
+void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn);
+void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma);
+void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* const* dout);

@@ -1,0 +1,571 @@
+// Device patch builder: ordered cell/facet fan around every vertex, patch
+// classification per RHS, reversed-facet flags; plus the expansion of the SE
+// 4-plane DOF map for bit-exact comparison with the reference layout.
+//
+// Reference semantics (not code): se::OrientedPatch::initialize_patch
+// `se/Patch.cpp:406-635`, next_facet `:682-759`, reversion_required `:106-128`,
+// Patch::create_subdofmap `se/Patch.hpp:792-898`, set_assembly_informations
+// `:710-789`, reversed-facet detection `se/solve_patch_semiexplt.hpp:325-389`,
+// set_boundary_markers `se/assembly.hpp:46-98`.
+//
+// One thread per patch: the walk around a vertex is inherently sequential
+// (<= 16 steps) while the ~1e6..3e7 patches are independent; all loads are 4-byte
+// gathers from CSR arrays that stay L2 resident.  The builder runs once per
+// eqlb_set_bcs, not per equilibration.
+#include "eqlb_internal.cuh"
+
+namespace
+{
+
+struct Fan
+{
+  int nc, nf;
+  int32_t cells[EQLB_NCMAX + 2];
+  int32_t fcts[EQLB_NCMAX + 2];
+  int8_t inod[EQLB_NCMAX + 2];
+  int8_t fl[2 * (EQLB_NCMAX + 1)];
+  int8_t type0;
+  int32_t fct_ep[2], fct_ef[2];
+};
+
+__device__ __forceinline__ int local_index3(const int32_t* __restrict__ arr3, int32_t val)
+{
+  return (arr3[0] == val) ? 0 : ((arr3[1] == val) ? 1 : 2);
+}
+
+// Ordered fan of cells / facets around `node`.
+__device__ void build_fan(const MeshView& m, const int8_t* __restrict__ facet_type0, int node, Fan& F)
+{
+  const int c0 = m.node_cell_off[node], c1 = m.node_cell_off[node + 1];
+  const int f0 = m.node_fct_off[node], f1 = m.node_fct_off[node + 1];
+  const int nc = c1 - c0, nf = f1 - f0;
+  F.nc = nc;
+  F.nf = nf;
+  F.type0 = EQLB_PATCH_INTERNAL;
+  F.fct_ep[0] = F.fct_ep[1] = F.fct_ef[0] = F.fct_ef[1] = -1;
+  int32_t fct_first = m.node_fct[f0];
+  if (nf > nc)
+  {
+    for (int i = f0; i < f1; ++i)
+    {
+      const int32_t id = m.node_fct[i];
+      const int8_t ft = facet_type0[id];
+      if (ft == EQLB_FCT_ESSNT_PRIMAL)
+      {
+        if (F.fct_ep[0] < 0)
+          F.fct_ep[0] = id;
+        else
+          F.fct_ep[1] = id;
+      }
+      else if (ft == EQLB_FCT_ESSNT_DUAL)
+      {
+        if (F.fct_ef[0] < 0)
+          F.fct_ef[0] = id;
+        else
+          F.fct_ef[1] = id;
+      }
+    }
+    if (F.fct_ef[0] < 0)
+    {
+      F.type0 = EQLB_PATCH_ESSNT_PRIMAL;
+      fct_first = F.fct_ep[0];
+    }
+    else
+    {
+      F.type0 = (F.fct_ep[0] < 0) ? EQLB_PATCH_ESSNT_DUAL : EQLB_PATCH_MIXED;
+      fct_first = F.fct_ef[0];
+    }
+  }
+  const bool internal = (F.type0 == EQLB_PATCH_INTERNAL);
+  int lloop = nc + 1;
+  if (internal)
+  {
+    F.fcts[1] = fct_first;
+    F.cells[1] = m.fct_cell[m.fct_cell_off[fct_first] + 1];
+  }
+  else
+  {
+    F.fcts[0] = fct_first;
+    const int32_t c = m.fct_cell[m.fct_cell_off[fct_first]];
+    F.cells[1] = c;
+    const int lf = local_index3(m.cell_fct + 3 * c, fct_first);
+    F.fl[0] = lf;
+    F.fl[1] = lf;
+    const int v = local_index3(m.cell_node + 3 * c, node);
+    // next facet: the facet of the cell, other than lf, that contains the node
+    // (facet f is opposite vertex f)  == result of se/Patch.cpp:682-759
+    F.fcts[1] = m.cell_fct[3 * c + (3 - lf - v)];
+    lloop = nc;
+  }
+  for (int a = 1; a < lloop; ++a)
+  {
+    const int32_t fct_a = F.fcts[a], cell_a = F.cells[a];
+    const int o = m.fct_cell_off[fct_a];
+    const int32_t ca = m.fct_cell[o], cb = m.fct_cell[o + 1];
+    const int32_t cell_ap1 = (ca == cell_a) ? cb : ca;
+    F.cells[a + 1] = cell_ap1;
+    const int lf_ap1 = local_index3(m.cell_fct + 3 * cell_ap1, fct_a);
+    F.fl[2 * a] = local_index3(m.cell_fct + 3 * cell_a, fct_a);
+    F.fl[2 * a + 1] = lf_ap1;
+    F.inod[a] = local_index3(m.cell_node + 3 * cell_a, node);
+    const int v = local_index3(m.cell_node + 3 * cell_ap1, node);
+    F.fcts[a + 1] = m.cell_fct[3 * cell_ap1 + (3 - lf_ap1 - v)];
+  }
+  if (!internal)
+  {
+    F.inod[nc] = local_index3(m.cell_node + 3 * F.cells[nc], node);
+    const int lf = local_index3(m.cell_fct + 3 * F.cells[nc], F.fcts[nc]);
+    F.fl[2 * nc] = lf;
+    F.fl[2 * nc + 1] = lf;
+  }
+  else
+  {
+    F.cells[0] = F.cells[nc];
+    F.cells[nc + 1] = F.cells[1];
+    F.inod[0] = F.inod[nc];
+    F.inod[nc + 1] = F.inod[1];
+    F.fcts[0] = F.fcts[nf];
+    F.fl[0] = F.fl[2 * nf];
+    F.fl[1] = F.fl[2 * nf + 1];
+  }
+}
+
+// patch type of RHS i (se/Patch.cpp:487-526)
+__device__ __forceinline__ int8_t patch_type_rhs(const Fan& F, const int8_t* __restrict__ ft_i, int i)
+{
+  if (F.type0 == EQLB_PATCH_INTERNAL)
+    return EQLB_PATCH_INTERNAL;
+  if (i == 0)
+    return F.type0;
+  int32_t fa, fb;
+  if (F.type0 == EQLB_PATCH_ESSNT_PRIMAL)
+  {
+    fa = F.fct_ep[0];
+    fb = F.fct_ep[1];
+  }
+  else if (F.type0 == EQLB_PATCH_ESSNT_DUAL)
+  {
+    fa = F.fct_ef[0];
+    fb = F.fct_ef[1];
+  }
+  else
+  {
+    fa = F.fct_ef[0];
+    fb = F.fct_ep[0];
+  }
+  if (ft_i[fa] == ft_i[fb])
+    return (ft_i[fa] == EQLB_FCT_ESSNT_PRIMAL) ? EQLB_PATCH_ESSNT_PRIMAL : EQLB_PATCH_ESSNT_DUAL;
+  return EQLB_PATCH_MIXED;
+}
+
+// reversed(a, 0/1) flags (se/solve_patch_semiexplt.hpp:325-389)
+__device__ __forceinline__ void reversed_flags(const MeshView& m, const Fan& F, int a, bool& r0, bool& r1)
+{
+  const bool bnd = (F.type0 != EQLB_PATCH_INTERNAL);
+  const int32_t c = F.cells[a];
+  r0 = false;
+  r1 = false;
+  if (!(bnd && a == 1))
+  {
+    const int32_t c_am1 = F.cells[a - 1];
+    // local id of E_{a-1} in T_{a-1} = fl[2(a-1)] ; for the interior patch a-1 == 0
+    // maps to fl[0] (= fl[2 nf])
+    r0 = m.fct_perms[3 * c_am1 + F.fl[2 * (a - 1)]] != m.fct_perms[3 * c + F.fl[2 * a - 1]];
+  }
+  if (!(bnd && a == F.nc))
+  {
+    const int32_t c_ap1 = F.cells[a + 1];
+    r1 = m.fct_perms[3 * c + F.fl[2 * a]] != m.fct_perms[3 * c_ap1 + F.fl[2 * a + 1]];
+  }
+}
+
+__global__ void patch_builder_kernel(MeshView m, const int8_t* __restrict__ facet_type, int nrhs,
+                                     const int32_t* __restrict__ order, int npatch, size_t stride, int ncmax,
+                                     // compact records (colour order)
+                                     int32_t* __restrict__ pnode, uint8_t* __restrict__ pncells,
+                                     int32_t* __restrict__ pcell, uint8_t* __restrict__ pinfo,
+                                     uint8_t* __restrict__ prhs,
+                                     // expanded, reference layout (node order); may be null
+                                     int32_t* __restrict__ x_ncells, int32_t* __restrict__ x_cells,
+                                     int32_t* __restrict__ x_fcts, int8_t* __restrict__ x_inod,
+                                     int8_t* __restrict__ x_fl, int8_t* __restrict__ x_type,
+                                     uint8_t* __restrict__ x_rev, uint8_t* __restrict__ x_reversion)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npatch)
+    return;
+  const int node = order[i];
+  Fan F;
+  build_fan(m, facet_type, node, F);
+  const int nc = F.nc;
+  const bool internal = (F.type0 == EQLB_PATCH_INTERNAL);
+
+  if (pnode)
+  {
+    pnode[i] = node;
+    pncells[i] = (uint8_t)nc;
+  }
+  for (int a = 1; a <= nc; ++a)
+  {
+    bool r0, r1;
+    reversed_flags(m, F, a, r0, r1);
+    if (pcell)
+    {
+      pcell[(size_t)(a - 1) * stride + i] = F.cells[a];
+      pinfo[(size_t)(a - 1) * stride + i]
+          = (uint8_t)(F.inod[a] | (F.fl[2 * a - 1] << 2) | (F.fl[2 * a] << 4) | (r0 ? 64 : 0) | (r1 ? 128 : 0));
+    }
+    if (x_rev)
+    {
+      x_rev[((size_t)node * ncmax + (a - 1)) * 2] = r0;
+      x_rev[((size_t)node * ncmax + (a - 1)) * 2 + 1] = r1;
+    }
+  }
+  int8_t type_prev = 0;
+  for (int r = 0; r < nrhs; ++r)
+  {
+    const int8_t* ft = facet_type + (size_t)r * m.nfct;
+    const int8_t tp = patch_type_rhs(F, ft, r);
+    bool bc0 = false, bcn = false, rev = false;
+    if (!internal)
+    {
+      bc0 = ft[F.fcts[0]] == EQLB_FCT_ESSNT_DUAL;
+      bcn = ft[F.fcts[nc]] == EQLB_FCT_ESSNT_DUAL;
+      const bool req = (tp == EQLB_PATCH_ESSNT_DUAL || tp == EQLB_PATCH_MIXED);
+      if (r > 0 && req && (tp != type_prev || tp == EQLB_PATCH_MIXED) && !bc0)
+        rev = true;
+    }
+    type_prev = tp;
+    if (prhs)
+      prhs[(size_t)r * stride + i] = (uint8_t)(tp | (rev ? 4 : 0) | (bc0 ? 8 : 0) | (bcn ? 16 : 0));
+    if (x_type)
+      x_type[(size_t)node * nrhs + r] = tp;
+    if (x_reversion)
+      x_reversion[(size_t)node * nrhs + r] = rev;
+  }
+  if (x_ncells)
+    x_ncells[node] = nc;
+  const int lo = internal ? 0 : 1;
+  const int hi = internal ? nc + 2 : nc + 1;
+  if (x_cells)
+    for (int a = lo; a < hi; ++a)
+      x_cells[(size_t)node * (ncmax + 2) + a] = F.cells[a];
+  if (x_inod)
+    for (int a = lo; a < hi; ++a)
+      x_inod[(size_t)node * (ncmax + 2) + a] = F.inod[a];
+  if (x_fcts)
+    for (int a = 0; a < F.nf + (internal ? 1 : 0); ++a)
+      x_fcts[(size_t)node * (ncmax + 2) + a] = F.fcts[a];
+  if (x_fl)
+    for (int a = 0; a < 2 * F.nf + (internal ? 2 : 0); ++a)
+      x_fl[(size_t)node * 2 * (ncmax + 1) + a] = F.fl[a];
+}
+
+// ---------------------------------------------------------------------------
+// SE DOF-map expansion (parity evidence only; the hot kernel evaluates the same
+// index arithmetic on the fly instead of reading 4 planes of int32 from HBM)
+// ---------------------------------------------------------------------------
+__global__ void se_dofmap_kernel(MeshView m, const int8_t* __restrict__ facet_type, int nrhs, int npatch, int ncmax,
+                                 int k, int nrt, int nadd, int ndiv, int ndg_fct, int p, bool stress,
+                                 const int32_t* __restrict__ closure, const double* __restrict__ cellJ,
+                                 int32_t* __restrict__ dofmap, int32_t* __restrict__ projflux,
+                                 int8_t* __restrict__ bmarkers, int ndpc, int hzmax)
+{
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= npatch)
+    return;
+  Fan F;
+  build_fan(m, facet_type, node, F);
+  const int nc = F.nc, nf = F.nf;
+  const bool internal = (F.type0 == EQLB_PATCH_INTERNAL);
+  const int offs1 = k, offs2 = 2 * k, offs3 = 2 * k + nadd, offs4 = stress ? offs3 + 3 : offs3;
+  const bool out[3] = {false, true, false};
+  int32_t* dm = dofmap ? dofmap + (size_t)node * 4 * (ncmax + 2) * ndpc : nullptr;
+#define DM(pl, a, i) dm[((size_t)(pl) * (ncmax + 2) + (a)) * ndpc + (i)]
+  if (dm)
+  {
+    for (int pl = 0; pl < 4; ++pl)
+      for (int a = 0; a < nc + 2; ++a)
+        for (int i = 0; i < ndpc; ++i)
+          DM(pl, a, i) = 0;
+    for (int a = 1; a <= nc; ++a)
+    {
+      const int32_t cell = F.cells[a];
+      const int fl_m = F.fl[2 * a - 1], fl_p = F.fl[2 * a];
+      const int gdof = cell * nrt;
+      if (k == 1)
+      {
+        DM(0, a, 0) = fl_m;
+        DM(0, a, 1) = fl_p;
+        DM(1, a, 0) = gdof + fl_m;
+        DM(1, a, 1) = gdof + fl_p;
+      }
+      else
+      {
+        const int pd_m = (a - 1) * (k - 1);
+        const int pd_p = (internal && a == nc) ? 0 : pd_m + k - 1;
+        for (int ii = 0; ii < k; ++ii)
+        {
+          DM(0, a, ii) = fl_m * k + ii;
+          DM(0, a, offs1 + ii) = fl_p * k + ii;
+          DM(1, a, ii) = gdof + fl_m * k + ii;
+          DM(1, a, offs1 + ii) = gdof + fl_p * k + ii;
+          DM(2, a, ii) = ii == 0 ? 0 : pd_m + ii;
+          DM(2, a, offs1 + ii) = ii == 0 ? 0 : pd_p + ii;
+        }
+        for (int ii = 0; ii < nadd; ++ii)
+        {
+          DM(0, a, offs2 + ii) = 3 * k + ndiv + ii;
+          DM(1, a, offs2 + ii) = gdof + 3 * k + ndiv + ii;
+          DM(2, a, offs2 + ii) = nf * (k - 1) + 1 + (a - 1) * nadd + ii;
+          DM(3, a, offs2 + ii) = 1;
+        }
+        for (int ii = 0; ii < ndiv; ++ii)
+        {
+          DM(0, a, offs4 + ii) = 3 * k + ii;
+          DM(1, a, offs4 + ii) = gdof + 3 * k + ii;
+        }
+      }
+    }
+    if (stress)
+    {
+      // weak-symmetry constraint DOFs (se/Patch.hpp:621-708): slot offs3 = patch node,
+      // offs3+1 = outer node of E_a, offs3+2 = outer node of E_{a-1}
+      for (int a = 1; a <= nc; ++a)
+      {
+        const int32_t cell = F.cells[a];
+        DM(0, a, offs3) = F.inod[a];
+        DM(2, a, offs3) = 0;
+        DM(3, a, offs3) = 1;
+        // outer node of E_a
+        {
+          const int32_t fct = F.fcts[a];
+          const int32_t n0 = m.fct_node[2 * fct], n1 = m.fct_node[2 * fct + 1];
+          const int32_t nd = (n0 == node) ? n1 : n0;
+          DM(0, a, offs3 + 1) = local_index3(m.cell_node + 3 * cell, nd);
+          DM(2, a, offs3 + 1) = (!internal && a == nc) ? nf : a;
+          DM(3, a, offs3 + 1) = 1;
+        }
+        // outer node of E_{a-1}
+        {
+          const int32_t fct = F.fcts[a - 1];
+          const int32_t n0 = m.fct_node[2 * fct], n1 = m.fct_node[2 * fct + 1];
+          const int32_t nd = (n0 == node) ? n1 : n0;
+          DM(0, a, offs3 + 2) = local_index3(m.cell_node + 3 * cell, nd);
+          DM(2, a, offs3 + 2) = (a == 1) ? (internal ? nc : nf - 1) : a - 1;
+          DM(3, a, offs3 + 2) = 1;
+        }
+      }
+    }
+    // prefactors (plane 3), set_assembly_informations
+    for (int a = 1; a <= nc; ++a)
+    {
+      bool r0, r1;
+      reversed_flags(m, F, a, r0, r1);
+      const double* Jc = cellJ + 4 * (size_t)F.cells[a];
+      const double det = Jc[0] * Jc[3] - Jc[1] * Jc[2];
+      const int fl_m = F.fl[2 * a - 1], fl_p = F.fl[2 * a];
+      int p_m, p_p;
+      if (det < 0)
+      {
+        p_m = r0 ? DM(3, a - 1, k) : (out[fl_m] ? -1 : 1);
+        p_p = out[fl_p] ? 1 : -1;
+      }
+      else
+      {
+        p_m = r0 ? DM(3, a - 1, k) : (out[fl_m] ? 1 : -1);
+        p_p = out[fl_p] ? -1 : 1;
+      }
+      for (int i = 0; i < k; ++i)
+      {
+        DM(3, a, i) = p_m;
+        DM(3, a, k + i) = p_p;
+      }
+    }
+    if (internal)
+    {
+      bool r0, r1;
+      reversed_flags(m, F, 1, r0, r1);
+      if (r0)
+        for (int i = 0; i < k; ++i)
+          DM(3, 1, i) = DM(3, nc, k + i);
+      for (int pl = 0; pl < 4; ++pl)
+        for (int ii = 0; ii < ndpc; ++ii)
+        {
+          DM(pl, 0, ii) = DM(pl, nc, ii);
+          DM(pl, nc + 1, ii) = DM(pl, 1, ii);
+        }
+    }
+  }
+#undef DM
+  if (projflux)
+  {
+    int32_t* pf = projflux + (size_t)node * (ncmax + 1) * 2 * ndg_fct;
+    for (int a = 0; a < (nc + 1) * 2 * ndg_fct; ++a)
+      pf[a] = 0;
+    if (k > 1 && p > 0)
+    {
+      for (int a = 1; a <= nc; ++a)
+        for (int i = 0; i < ndg_fct; ++i)
+        {
+          pf[(a - 1) * 2 * ndg_fct + i] = closure[F.fl[2 * a - 1] * ndg_fct + i];
+          pf[a * 2 * ndg_fct + ndg_fct + i] = closure[F.fl[2 * a] * ndg_fct + i];
+        }
+      for (int i = 0; i < ndg_fct; ++i)
+      {
+        if (internal)
+        {
+          pf[nc * 2 * ndg_fct + i] = pf[i];
+          pf[ndg_fct + i] = pf[nc * 2 * ndg_fct + ndg_fct + i];
+        }
+        else
+        {
+          pf[ndg_fct + i] = pf[i];
+          pf[nc * 2 * ndg_fct + i] = pf[nc * 2 * ndg_fct + ndg_fct + i];
+        }
+      }
+    }
+  }
+  if (bmarkers)
+  {
+    const int hz = 1 + (k - 1) * nf + nadd * nc;
+    int8_t type_prev = 0;
+    for (int r = 0; r < nrhs; ++r)
+    {
+      const int8_t* ft = facet_type + (size_t)r * m.nfct;
+      const int8_t tp = patch_type_rhs(F, ft, r);
+      bool rev = false;
+      if (!internal)
+      {
+        const bool bc0 = ft[F.fcts[0]] == EQLB_FCT_ESSNT_DUAL;
+        const bool req = (tp == EQLB_PATCH_ESSNT_DUAL || tp == EQLB_PATCH_MIXED);
+        if (r > 0 && req && (tp != type_prev || tp == EQLB_PATCH_MIXED) && !bc0)
+          rev = true;
+      }
+      type_prev = tp;
+      int8_t* bm = bmarkers + ((size_t)node * nrhs + r) * hzmax;
+      for (int j = 0; j < hz; ++j)
+        bm[j] = 0;
+      if (tp == EQLB_PATCH_ESSNT_DUAL || tp == EQLB_PATCH_MIXED)
+      {
+        bm[0] = 1;
+        const int offset_En = nc * (k - 1);
+        for (int j = 1; j < k; ++j)
+        {
+          if (tp == EQLB_PATCH_ESSNT_DUAL)
+          {
+            bm[j] = 1;
+            bm[j + offset_En] = 1;
+          }
+          else if (rev)
+            bm[offset_En + j] = 1;
+          else
+            bm[j] = 1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void cellJ_kernel(int ncell, const double* __restrict__ x, const int32_t* __restrict__ cell_node,
+                             double* __restrict__ cellJ)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell)
+    return;
+  const int32_t n0 = cell_node[3 * c], n1 = cell_node[3 * c + 1], n2 = cell_node[3 * c + 2];
+  const double x0 = x[3 * n0], y0 = x[3 * n0 + 1];
+  double2* out = reinterpret_cast<double2*>(cellJ + 4 * (size_t)c);
+  out[0] = make_double2(x[3 * n1] - x0, x[3 * n2] - x0);          // J00 J01
+  out[1] = make_double2(x[3 * n1 + 1] - y0, x[3 * n2 + 1] - y0);  // J10 J11
+}
+
+} // namespace
+
+MeshView eqlb_handle::mesh_view() const
+{
+  MeshView m;
+  m.nnode = nnode;
+  m.ncell = ncell;
+  m.nfct = nfct;
+  m.x = d_x.p;
+  m.cell_node = d_cell_node.p;
+  m.cell_fct = d_cell_fct.p;
+  m.fct_node = d_fct_node.p;
+  m.fct_cell_off = d_fct_cell_off.p;
+  m.fct_cell = d_fct_cell.p;
+  m.node_cell_off = d_node_cell_off.p;
+  m.node_cell = d_node_cell.p;
+  m.node_fct_off = d_node_fct_off.p;
+  m.node_fct = d_node_fct.p;
+  m.fct_perms = d_fct_perms.p;
+  return m;
+}
+
+PatchView eqlb_handle::patch_view() const
+{
+  PatchView v;
+  v.npatch = nnode;
+  v.ncmax = ncmax;
+  v.nrhs = nrhs;
+  v.stride = pstride;
+  v.node = d_pnode.p;
+  v.ncells = d_pncells.p;
+  v.cell = d_pcell.p;
+  v.info = d_pinfo.p;
+  v.rhsinfo = d_prhs.p;
+  return v;
+}
+
+void launch_compute_cellJ(eqlb_handle* h)
+{
+  h->d_cellJ.alloc((size_t)h->ncell * 4);
+  const int bs = 256;
+  cellJ_kernel<<<(h->ncell + bs - 1) / bs, bs, 0, h->stream>>>(h->ncell, h->d_x.p, h->d_cell_node.p, h->d_cellJ.p);
+  CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+}
+
+void launch_patch_builder(eqlb_handle* h, int32_t* x_ncells, int32_t* x_cells, int32_t* x_fcts, int8_t* x_inod,
+                          int8_t* x_fl, int8_t* x_type, uint8_t* x_rev, uint8_t* x_reversion)
+{
+  const bool expand = x_ncells || x_cells || x_fcts || x_inod || x_fl || x_type || x_rev || x_reversion;
+  DevBuf<int32_t> d_order;
+  d_order.upload(h->h_order.data(), h->h_order.size());
+  const int bs = 128;
+  patch_builder_kernel<<<(h->nnode + bs - 1) / bs, bs, 0, h->stream>>>(
+      h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nnode, h->pstride, h->ncmax,
+      expand ? nullptr : h->d_pnode.p, h->d_pncells.p, expand ? nullptr : h->d_pcell.p, h->d_pinfo.p,
+      expand ? nullptr : h->d_prhs.p, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->launches++;
+}
+
+void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, int8_t* d_bmarkers, int ndpc, int hzmax)
+{
+  DevBuf<int32_t> d_closure;
+  std::vector<int32_t> closure(3 * h->ndg_fct);
+  // closure dofs of P_p facets: vertices (a,b) of facet f then edge interior dofs
+  const int fv[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+  for (int f = 0; f < 3; ++f)
+  {
+    if (h->p == 0)
+      closure[f] = 0;
+    else
+    {
+      closure[f * h->ndg_fct] = fv[f][0];
+      closure[f * h->ndg_fct + 1] = fv[f][1];
+      for (int i = 0; i < h->p - 1; ++i)
+        closure[f * h->ndg_fct + 2 + i] = 3 + f * (h->p - 1) + i;
+    }
+  }
+  d_closure.upload(closure.data(), closure.size());
+  const int bs = 128;
+  se_dofmap_kernel<<<(h->nnode + bs - 1) / bs, bs, 0, h->stream>>>(
+      h->mesh_view(), h->d_facet_type.p, h->nrhs, h->nnode, h->ncmax, h->k, h->nrt, h->nadd, h->ndiv, h->ndg_fct, h->p,
+      (h->flags & EQLB_FLAG_STRESS) != 0, d_closure.p, h->d_cellJ.p, d_dofmap, d_projflux, d_bmarkers, ndpc, hzmax);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->launches++;
+}

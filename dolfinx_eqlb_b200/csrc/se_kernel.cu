@@ -1,0 +1,714 @@
+// Semi-explicit equilibration, fused patch kernel (step 1 + step 2 + scatter).
+//
+// Reference semantics: se/solve_patch_semiexplt.hpp:212-1163 (+ assembly.hpp,
+// fluxmin_kernel.hpp, PatchData.hpp, BoundaryData.cpp:686-745).  B200 design
+// (DESIGN.md "SE kernel"):
+//  * one thread per patch, patches of one colour per launch (no two patches of a
+//    colour share a cell -> plain, deterministic += into the global DRT vector);
+//  * no quadrature loops: on affine cells every integral of the reference is a
+//    contraction of exact reference-cell tables with the cell Jacobian:
+//      facet moments   m[j]  = sum_i W[f][v][j][i] (N_f . G_i),  N_f = adj(J)^T n_ref
+//      cell moments    cm[t] = sum_i detJ f_i C[v][t][i] - (adj(J)^T D[v][t][i]) . G_i
+//      RT mass matrix  M_c   = (g00 M00 + g01 (M01+M10) + g11 M11)/|detJ|, g = J^T J
+//    tables live in shared memory (a few KB), inputs are gathered straight from
+//    HBM/L2 (every cell is touched by its 3 vertex patches);
+//  * the patch system (SPD, hz <= 1+(k-1) n_f + nadd n_c) is factorised by an
+//    in-thread Cholesky.
+#include <cstdio>
+
+#include "eqlb_internal.cuh"
+
+namespace
+{
+
+__device__ __constant__ double c_nref[3][2] = {{-1.0, -1.0}, {-1.0, 0.0}, {0.0, 1.0}};
+
+template <int K>
+struct SeDims
+{
+  static constexpr int k = K;
+  static constexpr int ndiv = K * (K + 1) / 2 - 1;
+  static constexpr int nadd = (K - 1) * (K - 2) / 2;
+  static constexpr int nrt = K * (K + 2);
+  static constexpr int nact = 2 * K + nadd;         // rows of the cell block (facet + add functions)
+  static constexpr int ncol = 2 * K + nadd + ndiv;  // columns (active coefficients)
+  static constexpr int nz = 2 * K + nadd - 1;       // H(div=0) functions per cell
+};
+
+// packed lower-triangular index
+__device__ __forceinline__ int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <int K, int NDG, int NCMAX>
+__global__ void __launch_bounds__(128)
+se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __restrict__ cellJ,
+                const int32_t* __restrict__ dgmap, int nrhs, RhsPtrs ptrs,
+                const double* __restrict__ bflux, size_t bflux_stride, int use_atomics)
+{
+  using D = SeDims<K>;
+  constexpr int k = K, ndiv = D::ndiv, nadd = D::nadd, nrt = D::nrt, nact = D::nact, ncol = D::ncol, nz = D::nz;
+  constexpr int HZ = 1 + (K - 1) * (NCMAX + 1) + nadd * NCMAX;
+  constexpr int NT = 1 + ndiv;
+
+  extern __shared__ double s_tab[];
+  for (int i = threadIdx.x; i < tv.ndoubles; i += blockDim.x)
+    s_tab[i] = tv.data[i];
+  __syncthreads();
+  const double* __restrict__ t_mass = s_tab + tv.o_rt_mass;    // [3][nrt][nrt]
+  const double* __restrict__ t_fmom = s_tab + tv.o_fct_mom;    // [3][3][k][NDG]
+  const double* __restrict__ t_cmf = s_tab + tv.o_cell_mom_f;  // [3][NT][NDG]
+  const double* __restrict__ t_cmg = s_tab + tv.o_cell_mom_g;  // [3][NT][NDG][2]
+  const double* __restrict__ t_bc = s_tab + tv.o_bc_mat;       // [3][3][k][k]
+  const double* __restrict__ t_trafo = s_tab + tv.o_trafo;     // [k][k]
+
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= count)
+    return;
+  const size_t ip = (size_t)first + tid;
+  const int nc = pv.ncells[ip];
+
+  // ---- per-cell geometry / orientation (independent of the RHS) ----
+  int32_t cell[NCMAX];
+  uint8_t info[NCMAX];
+  double gm[NCMAX][3];   // J^T J / |detJ|
+  double adj[NCMAX][4];  // adj(J) = detJ * K
+  double detJ[NCMAX];
+  double pm[NCMAX], pp[NCMAX];  // prefactor_dof(a, 0/1)
+#pragma unroll 1
+  for (int a = 0; a < nc; ++a)
+  {
+    const int32_t c = pv.cell[(size_t)a * pv.stride + ip];
+    cell[a] = c;
+    const uint8_t inf = pv.info[(size_t)a * pv.stride + ip];
+    info[a] = inf;
+    const double2 j0 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c];
+    const double2 j1 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c + 1];
+    const double J00 = j0.x, J01 = j0.y, J10 = j1.x, J11 = j1.y;
+    const double det = J00 * J11 - J01 * J10;
+    const double iad = 1.0 / fabs(det);
+    detJ[a] = det;
+    adj[a][0] = J11;
+    adj[a][1] = -J01;
+    adj[a][2] = -J10;
+    adj[a][3] = J00;
+    gm[a][0] = (J00 * J00 + J10 * J10) * iad;
+    gm[a][1] = (J00 * J01 + J10 * J11) * iad;
+    gm[a][2] = (J01 * J01 + J11 * J11) * iad;
+    const double sgn = det > 0.0 ? 1.0 : -1.0;
+    const int fm = (inf >> 2) & 3, fp = (inf >> 4) & 3;
+    pm[a] = (fm == 1) ? sgn : -sgn;  // reference normal outward only on facet 1
+    pp[a] = (fp == 1) ? sgn : -sgn;
+  }
+
+  double mm[NCMAX][K], mp[NCMAX][K];  // own-side facet moments on E_{a-1} / E_a
+  double cm[NCMAX][NT];               // cell moments
+  double cf[NCMAX][ncol];             // sigma-tilde coefficients: [E_{a-1} (k)][E_a (k)][add][div]
+  double A[HZ * (HZ + 1) / 2];
+  double L[HZ];
+
+  for (int r = 0; r < nrhs; ++r)
+  {
+    const double* __restrict__ G = ptrs.G[r];
+    const double* __restrict__ Fv = ptrs.F[r];
+    const uint8_t ri = pv.rhsinfo[(size_t)r * pv.stride + ip];
+    const int ptype = ri & 3;
+    const bool reversion = (ri & 4) != 0;
+    const bool bc_e0 = (ri & 8) != 0, bc_en = (ri & 16) != 0;
+    const bool internal = (ptype == EQLB_PATCH_INTERNAL);
+    const int nf = internal ? nc : nc + 1;
+    const int hz = 1 + (k - 1) * nf + nadd * nc;
+
+    // ---- moments of every cell ----
+#pragma unroll 1
+    for (int a = 0; a < nc; ++a)
+    {
+      const int32_t c = cell[a];
+      const int v = info[a] & 3, fm = (info[a] >> 2) & 3, fp = (info[a] >> 4) & 3;
+      const double* ad = adj[a];
+      // N_f = adj(J)^T n_ref[f]
+      const double nmx = c_nref[fm][0] * ad[0] + c_nref[fm][1] * ad[2];
+      const double nmy = c_nref[fm][0] * ad[1] + c_nref[fm][1] * ad[3];
+      const double npx = c_nref[fp][0] * ad[0] + c_nref[fp][1] * ad[2];
+      const double npy = c_nref[fp][0] * ad[1] + c_nref[fp][1] * ad[3];
+#pragma unroll
+      for (int j = 0; j < k; ++j)
+      {
+        mm[a][j] = 0.0;
+        mp[a][j] = 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        cm[a][t] = 0.0;
+      const double* wm = t_fmom + ((fm * 3 + v) * k) * NDG;
+      const double* wp = t_fmom + ((fp * 3 + v) * k) * NDG;
+      const double* cf_ = t_cmf + (v * NT) * NDG;
+      const double* cg_ = t_cmg + (v * NT) * NDG * 2;
+#pragma unroll
+      for (int i = 0; i < NDG; ++i)
+      {
+        const size_t dof = dgmap ? (size_t)dgmap[(size_t)c * NDG + i] : (size_t)c * NDG + i;
+        const double2 g = reinterpret_cast<const double2*>(G)[dof];
+        const double fi = Fv[dof];
+        const double gnm = nmx * g.x + nmy * g.y;
+        const double gnp = npx * g.x + npy * g.y;
+        // adj^T applied to reference gradients: d/dx_phys * detJ
+        const double a0 = ad[0] * g.x + ad[1] * g.y;  // multiplies d/dxhat
+        const double a1 = ad[2] * g.x + ad[3] * g.y;  // multiplies d/dyhat
+        const double fd = detJ[a] * fi;
+#pragma unroll
+        for (int j = 0; j < k; ++j)
+        {
+          mm[a][j] += wm[j * NDG + i] * gnm;
+          mp[a][j] += wp[j * NDG + i] * gnp;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          cm[a][t] += fd * cf_[t * NDG + i] - a0 * cg_[(t * NDG + i) * 2] - a1 * cg_[(t * NDG + i) * 2 + 1];
+      }
+    }
+
+    // ---- step 1: explicit sweep ----
+    double c_prev = 0.0, c_t1_e0 = 0.0;
+#pragma unroll 1
+    for (int a = 0; a < nc; ++a)
+    {
+#pragma unroll
+      for (int i = 0; i < ncol; ++i)
+        cf[a][i] = 0.0;
+      const bool first_c = (a == 0), last_c = (a == nc - 1);
+      const bool on_bnd = !internal && (first_c || last_c);
+      bool has_bc = false;
+      if (on_bnd)
+      {
+        if (ptype == EQLB_PATCH_ESSNT_DUAL)
+          has_bc = true;
+        else if (ptype == EQLB_PATCH_MIXED)
+          has_bc = first_c ? bc_e0 : bc_en;  // (nc >= 2, so first/last are distinct cells)
+      }
+      const int v = info[a] & 3, fm = (info[a] >> 2) & 3, fp = (info[a] >> 4) & 3;
+      const bool rev1 = (info[a] & 128) != 0;
+      const double sgn = detJ[a] > 0.0 ? 1.0 : -1.0;
+
+      double c_m = -c_prev;
+      double surf = 0.0;
+
+      // patch boundary condition (RT interpolant of hat * boundary flux)
+      if (has_bc)
+      {
+        const int fb = first_c ? fm : fp;
+        const double* bsrc = bflux + (size_t)r * bflux_stride + (size_t)cell[a] * nrt + fb * k;
+        double b[K], bv[K];
+        int nzero = 0;
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+        {
+          b[i] = bsrc[i];
+          if (fabs(b[i]) < 1e-7)
+            ++nzero;
+        }
+#pragma unroll
+        for (int j = 0; j < k; ++j)
+        {
+          double s = 0.0;
+          if (nzero < k)
+          {
+#pragma unroll
+            for (int i = 0; i < k; ++i)
+              s += t_bc[((fb * 3 + v) * k + j) * k + i] * b[i];
+          }
+          bv[j] = s;
+        }
+        if (first_c)
+          c_m += pm[a] * bv[0];
+#pragma unroll
+        for (int j = 1; j < k; ++j)
+          cf[a][(first_c ? 0 : k) + j] += bv[j];
+        if (reversion)
+          c_t1_e0 -= pp[a] * bv[0];
+      }
+
+      // facet E_{a-1}: zero-order jump contribution
+      if (!first_c)
+      {
+        // tau * m^+_{a-1}[0] - m^-_a[0], tau = -pp_{a-1} pm_a
+        surf = -mm[a][0] - pp[a - 1] * pm[a] * mp[a - 1][0];
+      }
+      else if (!internal)
+      {
+        if (has_bc || ptype == EQLB_PATCH_MIXED)
+        {
+          const double sg = (ptype == EQLB_PATCH_MIXED && !has_bc) ? 1.0 : -1.0;
+#pragma unroll
+          for (int j = 1; j < k; ++j)
+            cf[a][j] += sg * mm[a][j];
+          if (has_bc)
+            surf = -mm[a][0];
+        }
+      }
+      c_m += pm[a] * surf;
+      c_t1_e0 -= pm[a] * surf;
+
+      // cell integral
+      const double vol = sgn * cm[a][0];
+      const double c_p = -c_m + vol;
+      c_t1_e0 += vol;
+
+      // boundary contribution to c_t1_e0 on the last facet (mixed patch whose E_0
+      // lies on the Dirichlet boundary)
+      if (on_bnd && last_c && reversion)
+        c_t1_e0 -= pp[a] * (has_bc ? -1.0 : 1.0) * mp[a][0];
+
+      // higher-order moments on E_a
+      if (k > 1)
+      {
+        double h[K];
+        if (on_bnd && last_c)
+        {
+          const double pf = has_bc ? -1.0 : 1.0;
+#pragma unroll
+          for (int j = 1; j < k; ++j)
+            h[j] = pf * mp[a][j];
+        }
+        else
+        {
+          const int an = (a == nc - 1) ? 0 : a + 1;
+          const double tau = -pp[a] * pm[an];
+          double mt[K];
+          if (rev1)
+          {
+            // moments of the T_{a+1}-side trace w.r.t. the facet parameter of T_a:
+            // s' = 1 - s  ->  binomial transform
+#pragma unroll
+            for (int j = 0; j < k; ++j)
+            {
+              double s = 0.0;
+              double binom = 1.0;
+#pragma unroll
+              for (int i = 0; i <= j; ++i)
+              {
+                s += ((i & 1) ? -binom : binom) * mm[an][i];
+                binom = binom * (double)(j - i) / (double)(i + 1);
+              }
+              mt[j] = s;
+            }
+          }
+          else
+          {
+#pragma unroll
+            for (int j = 0; j < k; ++j)
+              mt[j] = mm[an][j];
+          }
+          const bool corr = rev1 && !last_c;
+          const double j0 = tau * mt[0] - mp[a][0];
+#pragma unroll
+          for (int j = 1; j < k; ++j)
+          {
+            h[j] = tau * mt[j] - mp[a][j];
+            if (corr)
+              h[j] += -j0 + pm[an] * c_p;
+          }
+        }
+#pragma unroll
+        for (int j = 1; j < k; ++j)
+          cf[a][k + j] += h[j];
+#pragma unroll
+        for (int t = 0; t < ndiv; ++t)
+          cf[a][2 * k + nadd + t] += cm[a][1 + t];
+      }
+      cf[a][0] += pm[a] * c_m;
+      cf[a][k] += pp[a] * c_p;
+#ifdef EQLB_DEBUG
+      if (reversion)
+        printf("DBG2 node %d rhs %d a %d c_m %.8f c_p %.8f surf %.8f vol %.8f has_bc %d cf0 %.8f cfk %.8f\n", pv.node[ip], r, a, c_m,
+               c_p, surf, vol, (int)has_bc, cf[a][0], cf[a][k]);
+#endif
+      c_prev = c_p;
+    }
+#ifdef EQLB_DEBUG
+    if (reversion)
+    {
+      printf("DBG node %d rhs %d nc %d type %d ct1e0 %.10f pm0 %f pp0 %f pm1 %f pp1 %f mm0 %.6f mp0 %.6f mm1 %.6f mp1 %.6f cm0 %.6f cm1 %.6f\n",
+             pv.node[ip], r, nc, ptype, c_t1_e0, pm[0], pp[0], pm[1], pp[1], mm[0][0], mp[0][0], mm[1][0], mp[1][0], cm[0][0], cm[1][0]);
+    }
+#endif
+    if (reversion)
+    {
+#pragma unroll 1
+      for (int a = 0; a < nc; ++a)
+      {
+        cf[a][0] += pm[a] * c_t1_e0;
+        cf[a][k] -= pp[a] * c_t1_e0;
+        if ((info[a] & 128) && a != nc - 1)
+#pragma unroll
+          for (int j = 1; j < k; ++j)
+            cf[a][k + j] -= pm[a + 1] * c_t1_e0;
+      }
+    }
+
+    // ---- step 2: assemble the patch system ----
+    const bool req_bc = (ptype == EQLB_PATCH_ESSNT_DUAL || ptype == EQLB_PATCH_MIXED);
+    const int offset_En = nc * (k - 1);
+    auto marked = [&](int pd) -> bool
+    {
+      if (!req_bc)
+        return false;
+      if (pd == 0)
+        return true;
+      if (pd >= 1 + (k - 1) * nf)
+        return false;
+      const bool onE0 = pd < k;
+      const bool onEn = pd > offset_En && pd < offset_En + k;
+      if (ptype == EQLB_PATCH_ESSNT_DUAL)
+        return onE0 || onEn;
+      return reversion ? onEn : onE0;
+    };
+    for (int i = 0; i < hz * (hz + 1) / 2; ++i)
+      A[i] = 0.0;
+    for (int i = 0; i < hz; ++i)
+      L[i] = 0.0;
+
+#pragma unroll 1
+    for (int a = 0; a < nc; ++a)
+    {
+      const int fm = (info[a] >> 2) & 3, fp = (info[a] >> 4) & 3;
+      const bool rev0 = (info[a] & 64) != 0;
+      // reference dof of active row/col q
+      auto rdof = [&](int q) -> int
+      {
+        if (q < k)
+          return fm * k + q;
+        if (q < 2 * k)
+          return fp * k + (q - k);
+        if (q < 2 * k + nadd)
+          return 3 * k + ndiv + (q - 2 * k);
+        return 3 * k + (q - 2 * k - nadd);
+      };
+      // cell block MB[nact][ncol] of the physical RT mass matrix
+      double MB[nact][ncol];
+      const double g0 = gm[a][0], g1 = gm[a][1], g2 = gm[a][2];
+#pragma unroll
+      for (int q = 0; q < nact; ++q)
+      {
+        const int rq = rdof(q);
+#pragma unroll
+        for (int s = 0; s < ncol; ++s)
+        {
+          const int rs = rdof(s);
+          const int o = rq * nrt + rs;
+          MB[q][s] = g0 * t_mass[o] + g1 * t_mass[nrt * nrt + o] + g2 * t_mass[2 * nrt * nrt + o];
+        }
+      }
+      // y = MB * cf  (untransformed rows)
+      double y[nact];
+#pragma unroll
+      for (int q = 0; q < nact; ++q)
+      {
+        double s = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < ncol; ++c2)
+          s += MB[q][c2] * cf[a][c2];
+        y[q] = s;
+      }
+      // reversed E_{a-1}: transform the test/trial functions of that facet
+      if (rev0)
+      {
+        double tmp[K];
+        // rows
+#pragma unroll
+        for (int s = 0; s < nact; ++s)
+        {
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+          {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < k; ++j)
+              acc += t_trafo[i * k + j] * MB[j][s];
+            tmp[i] = acc;
+          }
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+            MB[i][s] = tmp[i];
+        }
+        // columns
+#pragma unroll
+        for (int q = 0; q < nact; ++q)
+        {
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+          {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < k; ++j)
+              acc += t_trafo[i * k + j] * MB[q][j];
+            tmp[i] = acc;
+          }
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+            MB[q][i] = tmp[i];
+        }
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+        {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < k; ++j)
+            acc += t_trafo[i * k + j] * y[j];
+          tmp[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+          y[i] = tmp[i];
+      }
+      // signs: p_ea = -pp_a ; p_eam1 = rev0 ? -pp_{a-1} : pm_a
+      const int am = (a == 0) ? nc - 1 : a - 1;
+      const double p_ea = -pp[a];
+      const double p_em = rev0 ? -pp[am] : pm[a];
+      // sub-basis function i (0..nz-1) = sum of up to two signed active rows
+      //   i <  k-1      : p_em * row(i+1)
+      //   i == k-1      : p_em * row(0) + p_ea * row(k)          (d0)
+      //   k <= i < 2k-1 : p_ea * row(i+1)
+      //   i >= 2k-1     : row(i+1)                                (additional)
+      auto sgn_of = [&](int q) -> double { return q < k ? p_em : (q < 2 * k ? p_ea : 1.0); };
+      // patch-local dof of sub-basis function i
+      auto pdof = [&](int i) -> int
+      {
+        if (i < k - 1)
+          return a * (k - 1) + i + 1;
+        if (i == k - 1)
+          return 0;
+        if (i < 2 * k - 1)
+          return ((internal && a == nc - 1) ? 0 : (a + 1) * (k - 1)) + (i - k + 1);
+        return nf * (k - 1) + 1 + a * nadd + (i - (2 * k - 1));
+      };
+      // Te(i, j) and load(i)
+#pragma unroll
+      for (int i = 0; i < nz; ++i)
+      {
+        const int qi = i + 1;
+        double li = (i == k - 1) ? -(p_em * y[0] + p_ea * y[k]) : -sgn_of(qi) * y[qi];
+        const int di = pdof(i);
+        const bool bi = marked(di);
+        if (bi)
+        {
+          L[di] = 0.0;
+          A[tri(di, di)] = 1.0;
+          continue;
+        }
+        L[di] += li;
+#pragma unroll
+        for (int j = 0; j < nz; ++j)
+        {
+          const int dj = pdof(j);
+          if (dj > di)
+            continue;  // lower triangle only (A symmetric)
+          if (marked(dj))
+            continue;
+          const int qj = j + 1;
+          double val;
+          if (i == k - 1 && j == k - 1)
+            val = MB[0][0] + MB[k][k] + 2.0 * p_em * p_ea * MB[0][k];
+          else if (i == k - 1)
+            val = sgn_of(qj) * (p_em * MB[0][qj] + p_ea * MB[k][qj]);
+          else if (j == k - 1)
+            val = sgn_of(qi) * (p_em * MB[qi][0] + p_ea * MB[qi][k]);
+          else
+            val = sgn_of(qi) * sgn_of(qj) * MB[qi][qj];
+          // each unordered pair of distinct patch dofs appears twice per cell (i,j)
+          // and (j,i): keep the one with dj <= di; pairs with di == dj and i != j
+          // cannot occur (distinct functions of a cell have distinct patch dofs)
+          A[tri(di, dj)] += val;
+        }
+      }
+    }
+
+    // ---- Cholesky solve ----
+    if (k == 1)
+    {
+      L[0] = L[0] / A[0];
+    }
+    else
+    {
+      for (int j = 0; j < hz; ++j)
+      {
+        double d = A[tri(j, j)];
+        for (int q = 0; q < j; ++q)
+          d -= A[tri(j, q)] * A[tri(j, q)];
+        d = sqrt(d);
+        A[tri(j, j)] = d;
+        const double id = 1.0 / d;
+        for (int i = j + 1; i < hz; ++i)
+        {
+          double s = A[tri(i, j)];
+          for (int q = 0; q < j; ++q)
+            s -= A[tri(i, q)] * A[tri(j, q)];
+          A[tri(i, j)] = s * id;
+        }
+      }
+      for (int i = 0; i < hz; ++i)
+      {
+        double s = L[i];
+        for (int q = 0; q < i; ++q)
+          s -= A[tri(i, q)] * L[q];
+        L[i] = s / A[tri(i, i)];
+      }
+      for (int i = hz - 1; i >= 0; --i)
+      {
+        double s = L[i];
+        for (int q = i + 1; q < hz; ++q)
+          s -= A[tri(q, i)] * L[q];
+        L[i] = s / A[tri(i, i)];
+      }
+    }
+
+#ifdef EQLB_DEBUG
+    if (reversion)
+      printf("DBG3 node %d rhs %d u0 %.8f A0 %.8f req_bc %d hz %d\n", pv.node[ip], r, L[0], A[0], (int)req_bc, hz);
+#endif
+    // ---- map back to cell coefficients and accumulate ----
+    double* __restrict__ sig = ptrs.S[r];
+#pragma unroll 1
+    for (int a = 0; a < nc; ++a)
+    {
+      const int fm = (info[a] >> 2) & 3, fp = (info[a] >> 4) & 3;
+      const bool rev0 = (info[a] & 64) != 0;
+      const int am = (a == 0) ? nc - 1 : a - 1;
+      const double p_ea = -pp[a];
+      const double p_em = rev0 ? -pp[am] : pm[a];
+      // slot -> patch dof (slot 0 and slot k are d0)
+      double um[K], up[K];
+#pragma unroll
+      for (int j = 0; j < k; ++j)
+      {
+        const int pd_m = (j == 0) ? 0 : a * (k - 1) + j;
+        const int pd_p = (j == 0) ? 0 : ((internal && a == nc - 1) ? 0 : (a + 1) * (k - 1)) + j;
+        um[j] = p_em * L[pd_m];
+        up[j] = p_ea * L[pd_p];
+      }
+      if (rev0)
+      {
+        double tmp[K];
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+        {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < k; ++j)
+            acc += t_trafo[j * k + i] * um[j];
+          tmp[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+          um[i] = tmp[i];
+      }
+      double* dst = sig + (size_t)cell[a] * nrt;
+      if (use_atomics)
+      {
+#pragma unroll
+        for (int j = 0; j < k; ++j)
+        {
+          atomicAdd(dst + fm * k + j, cf[a][j] + um[j]);
+          atomicAdd(dst + fp * k + j, cf[a][k + j] + up[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < nadd; ++i)
+          atomicAdd(dst + 3 * k + ndiv + i, cf[a][2 * k + i] + L[nf * (k - 1) + 1 + a * nadd + i]);
+#pragma unroll
+        for (int t = 0; t < ndiv; ++t)
+          atomicAdd(dst + 3 * k + t, cf[a][2 * k + nadd + t]);
+      }
+      else
+      {
+#pragma unroll
+        for (int j = 0; j < k; ++j)
+        {
+          dst[fm * k + j] += cf[a][j] + um[j];
+          dst[fp * k + j] += cf[a][k + j] + up[j];
+        }
+#pragma unroll
+        for (int i = 0; i < nadd; ++i)
+          dst[3 * k + ndiv + i] += cf[a][2 * k + i] + L[nf * (k - 1) + 1 + a * nadd + i];
+#pragma unroll
+        for (int t = 0; t < ndiv; ++t)
+          dst[3 * k + t] += cf[a][2 * k + nadd + t];
+      }
+    }
+  }
+}
+
+template <int K, int NDG>
+void launch_se_t(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
+{
+  RhsPtrs ptrs;
+  for (int r = 0; r < h->nrhs; ++r)
+  {
+    ptrs.G[r] = dG[r];
+    ptrs.F[r] = dF[r];
+    ptrs.S[r] = dSigma[r];
+  }
+  const PatchView pv = h->patch_view();
+  const int bs = 128;
+  const size_t smem = (size_t)h->tv.ndoubles * sizeof(double);
+  const bool atomics = (h->flags & EQLB_FLAG_ATOMIC) != 0;
+  auto kern8 = se_patch_kernel<K, NDG, 8>;
+  auto kern16 = se_patch_kernel<K, NDG, EQLB_NCMAX>;
+  auto kern = (h->ncmax <= 8) ? kern8 : kern16;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int32_t* dgmap = h->dg_identity ? nullptr : h->d_dg_dofmap.p;
+  const size_t bstride = (size_t)h->ncell * h->nrt;
+  if (atomics)
+  {
+    const int count = h->nnode;
+    kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, 0, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
+                                                        h->d_bflux.p, bstride, 1);
+    CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+  }
+  else
+  {
+    for (int c = 0; c < h->ncolours; ++c)
+    {
+      const int first = h->h_colour_off[c];
+      const int count = h->h_colour_off[c + 1] - first;
+      if (count == 0)
+        continue;
+      kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, first, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
+                                                          h->d_bflux.p, bstride, 0);
+      CUDA_CHECK(cudaGetLastError());
+      h->launches++;
+    }
+  }
+}
+
+} // namespace
+
+void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn)
+{
+  (void)dKorn;
+  const int key = h->k * 100 + h->ndg;
+  switch (key)
+  {
+  case 101:
+    launch_se_t<1, 1>(h, dG, dF, dSigma);
+    break;
+  case 201:
+    launch_se_t<2, 1>(h, dG, dF, dSigma);
+    break;
+  case 203:
+    launch_se_t<2, 3>(h, dG, dF, dSigma);
+    break;
+  case 301:
+    launch_se_t<3, 1>(h, dG, dF, dSigma);
+    break;
+  case 303:
+    launch_se_t<3, 3>(h, dG, dF, dSigma);
+    break;
+  case 306:
+    launch_se_t<3, 6>(h, dG, dF, dSigma);
+    break;
+  case 410:
+    launch_se_t<4, 10>(h, dG, dF, dSigma);
+    break;
+  default:
+    throw EqlbError(EQLB_ERR_INPUT, "SE kernel: unsupported (degree_flux, degree_dg) combination");
+  }
+}

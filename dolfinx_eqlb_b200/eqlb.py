@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's equilibration API for the hot path.
+
+Same names, argument meaning and error behaviour as
+`python/dolfinx_eqlb/eqlb/FluxEqlbSE.py`, `FluxEqlbEV.py`, `bcs.py` and the
+pybind entry points of `python/dolfinx_eqlb/wrappers.cpp:83-138`; DOLFINx
+objects are replaced by the plain arrays the pybind layer would extract from
+them (`Mesh` of `mesh.py`, DG coefficient vectors as numpy arrays or device
+pointers).  All numerics run in the CUDA library behind the C ABI
+(`include/eqlb_b200.h`); there is no CPU path in this module.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import cabi
+from .mesh import FACET_VERTS, Mesh
+from .tables import Tables, make_tables
+
+NORMAL_IS_OUTWARD = np.array([False, True, False])
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise RuntimeError(lib.eqlb_last_error().decode())
+
+
+class FluxBC:
+    """Essential flux boundary condition on a set of facets.
+
+    Stand-in for `dolfinx_eqlb.cpp.FluxBC` (`wrappers.cpp:144-232`) for the case the
+    reference evaluates by interpolation (`base/BoundaryData.cpp:580-597`): the
+    prescribed outward normal flux on facet i is the polynomial
+    sum_j coeffs[i, j] s^j in the facet parameter s of the adjacent cell."""
+
+    def __init__(self, facets, coeffs):
+        self.facets = np.ascontiguousarray(facets, dtype=np.int32)
+        self.coeffs = np.atleast_2d(np.asarray(coeffs, dtype=np.float64))
+        if self.coeffs.shape[0] != self.facets.shape[0]:
+            raise RuntimeError("FluxBC: one coefficient row per facet required")
+
+
+def fluxbc(facets, coeffs) -> FluxBC:
+    """`dolfinx_eqlb.eqlb.fluxbc` (`bcs.py:25-162`) for polynomial tractions."""
+    return FluxBC(facets, coeffs)
+
+
+class BoundaryData:
+    """State of `base::BoundaryData` after its constructor
+    (`base/BoundaryData.cpp:279-633`): facet types, boundary DOFs of the flux
+    function (hierarchic facet moments), local facet ids, node markers."""
+
+    def __init__(self, list_bcs, mesh: Mesh, tables: Tables, list_bfcts_prime, reconstruct_stress=False):
+        nrhs = len(list_bcs)
+        if len(list_bfcts_prime) != nrhs:
+            raise RuntimeError("Mismatching inputs!")
+        k, nrt = tables.k, tables.nrt
+        self.num_rhs = nrhs
+        self.facet_type = np.zeros((nrhs, mesh.nfct), dtype=np.int8)
+        self.bflux = [None] * nrhs
+        self.local_fct_id = np.zeros(mesh.nfct, dtype=np.int8)
+        cnt = np.zeros(mesh.nnode, dtype=np.int32)
+        x = mesh.x[:, :2]
+        for r in range(nrhs):
+            self.facet_type[r, np.asarray(list_bfcts_prime[r], dtype=np.int64)] = 1
+            for bc in list_bcs[r]:
+                if self.bflux[r] is None:
+                    self.bflux[r] = np.zeros(mesh.ncell * nrt)
+                f = bc.facets.astype(np.int64)
+                c = mesh.fct_cell[mesh.fct_cell_off[f]].astype(np.int64)
+                lf = np.argmax(mesh.cell_fct[c] == f[:, None], axis=1)
+                va = mesh.cell_node[c, FACET_VERTS[lf, 0]]
+                vb = mesh.cell_node[c, FACET_VERTS[lf, 1]]
+                length = np.linalg.norm(x[va] - x[vb], axis=1)
+                cn = mesh.cell_node[c]
+                J00 = x[cn[:, 1], 0] - x[cn[:, 0], 0]
+                J01 = x[cn[:, 2], 0] - x[cn[:, 0], 0]
+                J10 = x[cn[:, 1], 1] - x[cn[:, 0], 1]
+                J11 = x[cn[:, 2], 1] - x[cn[:, 0], 1]
+                sgn = np.sign(J00 * J11 - J01 * J10)
+                pre = np.where(NORMAL_IS_OUTWARD[lf], 1.0, -1.0) * sgn
+                ng = bc.coeffs.shape[1]
+                for j in range(k):
+                    mom = sum(bc.coeffs[:, i] / (i + j + 1) for i in range(ng))
+                    self.bflux[r][c * nrt + lf * k + j] = pre * length * mom
+                self.facet_type[r, f] = 2
+                self.local_fct_id[f] = lf
+                if reconstruct_stress and r < 2:
+                    np.add.at(cnt, mesh.fct_node[f].ravel(), 1)
+        self.node_on_stress_bnd = (cnt == 4).astype(np.int8) if reconstruct_stress else None
+
+
+def boundarydata(list_bcs, mesh, tables, list_bfcts_prime, equilibrate_stress=False) -> BoundaryData:
+    """`dolfinx_eqlb.eqlb.boundarydata` (`bcs.py:165-215`)."""
+    return BoundaryData(list_bcs, mesh, tables, list_bfcts_prime, equilibrate_stress)
+
+
+class _Problem:
+    """Owns the device-resident problem (C-ABI handle)."""
+
+    def __init__(self, mesh: Mesh, tables: Tables, nrhs: int, stress=False, atomic=False):
+        self.lib = cabi.load_library()
+        self.mesh, self.tables, self.nrhs = mesh, tables, nrhs
+        self._pm = cabi.PackedMesh(mesh, tables.ndg)
+        self._pt = cabi.PackedTables(tables)
+        flags = (1 if stress else 0) | (2 if atomic else 0)
+        self.stress = stress
+        h = C.c_void_p()
+        _check(self.lib, self.lib.eqlb_create(C.byref(self._pm.struct), C.byref(self._pt.struct), nrhs, flags, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.eqlb_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        _check(self.lib, self.lib.eqlb_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def set_bcs(self, bd: BoundaryData):
+        nob = bd.node_on_stress_bnd
+        _check(
+            self.lib,
+            self.lib.eqlb_set_bcs(
+                self.h,
+                bd.facet_type.ctypes.data_as(cabi.c_int8_p),
+                cabi.ptr_array(bd.bflux),
+                bd.local_fct_id.ctypes.data_as(cabi.c_int8_p),
+                nob.ctypes.data_as(cabi.c_int8_p) if nob is not None else cabi.c_int8_p(),
+            ),
+        )
+
+    def launch_count(self):
+        return int(self.lib.eqlb_launch_count(self.h))
+
+    # ---- integer maps (parity evidence) ----
+    def patch_dims(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(self.lib, self.lib.eqlb_patch_dims(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def patch_maps(self):
+        npatch, ncmax, ncol = self.patch_dims()
+        out = dict(
+            ncells=np.zeros(npatch, np.int32),
+            cells=np.zeros((npatch, ncmax + 2), np.int32),
+            fcts=np.zeros((npatch, ncmax + 2), np.int32),
+            inodes_local=np.zeros((npatch, ncmax + 2), np.int8),
+            fcts_local=np.zeros((npatch, 2 * (ncmax + 1)), np.int8),
+            type=np.zeros((npatch, self.nrhs), np.int8),
+            reversed=np.zeros((npatch, ncmax, 2), np.uint8),
+            reversion=np.zeros((npatch, self.nrhs), np.uint8),
+            colour=np.zeros(npatch, np.int32),
+        )
+        p = lambda a, t: a.ctypes.data_as(t)
+        _check(
+            self.lib,
+            self.lib.eqlb_get_patch_maps(
+                self.h, p(out["ncells"], cabi.c_int32_p), p(out["cells"], cabi.c_int32_p), p(out["fcts"], cabi.c_int32_p),
+                p(out["inodes_local"], cabi.c_int8_p), p(out["fcts_local"], cabi.c_int8_p), p(out["type"], cabi.c_int8_p),
+                p(out["reversed"], cabi.c_uint8_p), p(out["reversion"], cabi.c_uint8_p), p(out["colour"], cabi.c_int32_p),
+            ),
+        )
+        out["ncmax"], out["ncolours"] = ncmax, ncol
+        return out
+
+    def se_dofmaps(self):
+        npatch, ncmax, _ = self.patch_dims()
+        T = self.tables
+        ndpc = 2 * T.k + T.nadd + T.ndiv + (3 if self.stress else 0)
+        hzmax = 1 + (T.k - 1) * (ncmax + 1) + T.nadd * ncmax
+        dm = np.zeros((npatch, 4, ncmax + 2, ndpc), np.int32)
+        pf = np.zeros((npatch, ncmax + 1, 2 * T.ndg_fct), np.int32)
+        bm = np.zeros((npatch, self.nrhs, hzmax), np.int8)
+        a, b = C.c_int32(), C.c_int32()
+        _check(
+            self.lib,
+            self.lib.eqlb_get_se_dofmaps(
+                self.h, dm.ctypes.data_as(cabi.c_int32_p), pf.ctypes.data_as(cabi.c_int32_p),
+                bm.ctypes.data_as(cabi.c_int8_p), C.byref(a), C.byref(b),
+            ),
+        )
+        assert a.value == ndpc and b.value == hzmax
+        return dict(dofmap=dm, projflux_fct=pf, bmarkers=bm)
+
+
+def _as_ptr_list(arrs):
+    return [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+
+
+def reconstruct_fluxes_semiexplt(problem: _Problem, flux_hdiv, flux_dg, rhs_dg, korn=None):
+    """`cpp.reconstruct_fluxes_semiexplt[_with_kornconst]` (`wrappers.cpp:97-137`):
+    host numpy vectors, accumulated in place into `flux_hdiv`."""
+    lib = problem.lib
+    G, F = _as_ptr_list(flux_dg), _as_ptr_list(rhs_dg)
+    for s in flux_hdiv:
+        if not (isinstance(s, np.ndarray) and s.dtype == np.float64 and s.flags.c_contiguous):
+            raise RuntimeError("flux_hdiv must be contiguous float64 arrays (accumulated in place)")
+    if not (len(G) == len(F) == len(flux_hdiv) == problem.nrhs):
+        raise RuntimeError("Equilibration: Input sizes does not match")
+    kp = korn.ctypes.data_as(cabi.c_double_p) if korn is not None else cabi.c_double_p()
+    _check(lib, lib.eqlb_se_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), kp, 0))
+
+
+def reconstruct_fluxes_minimisation(problem: _Problem, flux_hdiv, flux_dg, rhs_dg):
+    """`cpp.reconstruct_fluxes_minimisation` (`wrappers.cpp:85-95`) for the fixed
+    forms of `FluxEqlbEV.py:116-133`."""
+    lib = problem.lib
+    G, F = _as_ptr_list(flux_dg), _as_ptr_list(rhs_dg)
+    if not (len(G) == len(F) == len(flux_hdiv) == problem.nrhs):
+        raise RuntimeError("Equilibration: Input sizes does not match")
+    _check(lib, lib.eqlb_ev_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), 0))
+
+
+class FluxEquilibrator:
+    """`eqlb/FluxEquilibrator.py:15-96`."""
+
+    def __init__(self, degree_flux: int, n_eqlbs: int, equilibrate_stress: bool):
+        self.degree_flux = degree_flux
+        self.n_fluxes = n_eqlbs
+        self.equilibrate_stresses = equilibrate_stress
+        self.list_flux = []
+        self.list_bfunctions = []
+        self.boundary_data = None
+
+
+class FluxEqlbSE(FluxEquilibrator):
+    """`eqlb/FluxEqlbSE.py:24-198` on top of the CUDA hot path."""
+
+    def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, equilibrate_stress=False,
+                 estimate_korn_constant=False, degree_proj=None, atomic=False):
+        super().__init__(degree_flux, len(list_rhs), equilibrate_stress)
+        if len(list_proj_flux) != self.n_fluxes:
+            raise RuntimeError("Mismatching inputs!")
+        self.mesh = msh
+        self.tables = make_tables(degree_flux, degree_proj)
+        self.list_rhs, self.list_proj_flux = list_rhs, list_proj_flux
+        self.estimate_korn_constant = estimate_korn_constant
+        self.korn_constants = np.zeros(msh.ncell) if estimate_korn_constant else None
+        self.problem = _Problem(msh, self.tables, self.n_fluxes, equilibrate_stress, atomic)
+        self.list_flux = [np.zeros(msh.ncell * self.tables.nrt) for _ in range(self.n_fluxes)]
+
+    def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
+        if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
+            raise RuntimeError("Mismatching inputs!")
+        self.boundary_data = boundarydata(list_bcs_flux, self.mesh, self.tables, list_bfct_prime, self.equilibrate_stresses)
+        self.list_bfunctions = self.boundary_data.bflux
+        self.problem.set_bcs(self.boundary_data)
+
+    def equilibrate_fluxes(self):
+        reconstruct_fluxes_semiexplt(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, self.korn_constants)
+        if self.estimate_korn_constant:
+            self.korn_constants[:] = np.sqrt(self.korn_constants)
+
+    def get_korn_constants(self):
+        if self.estimate_korn_constant:
+            return self.korn_constants
+        raise RuntimeError("Korn constants are not estimated!")
+
+
+class FluxEqlbEV(FluxEquilibrator):
+    """`eqlb/FluxEqlbEV.py:20-188` on top of the CUDA hot path; the flux lives in
+    the conforming hierarchic RT_k space ([facet dofs nfct*k][cell dofs])."""
+
+    def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux):
+        super().__init__(degree_flux, len(list_rhs), False)
+        if len(list_proj_flux) != self.n_fluxes:
+            raise RuntimeError("Missmatching inputs!")
+        self.mesh = msh
+        self.tables = make_tables(degree_flux)
+        self.list_rhs, self.list_proj_flux = list_rhs, list_proj_flux
+        self.problem = _Problem(msh, self.tables, self.n_fluxes, False, False)
+        k = degree_flux
+        self.ndofs = msh.nfct * k + msh.ncell * (k * k - k)
+        self.list_flux = [np.zeros(self.ndofs) for _ in range(self.n_fluxes)]
+
+    def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
+        if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
+            raise RuntimeError("Mismatching inputs!")
+        self.boundary_data = boundarydata(list_bcs_flux, self.mesh, self.tables, list_bfct_prime, False)
+        self.list_bfunctions = self.boundary_data.bflux
+        self.problem.set_bcs(self.boundary_data)
+
+    def equilibrate_fluxes(self):
+        reconstruct_fluxes_minimisation(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs)

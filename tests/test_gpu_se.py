@@ -1,0 +1,120 @@
+"""GPU parity tests of the SE path (call through the C ABI)."""
+
+import numpy as np
+import pytest
+
+import fem_mini as fm
+from common import PoissonCase, make_mesh
+from dolfinx_eqlb_b200 import eqlb
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10  # BASELINE.json north_star: flux DOFs within 1e-10 relative in FP64
+
+INT_KEYS = ["ncells", "cells", "fcts", "inodes_local", "fcts_local", "type", "reversed", "reversion"]
+
+
+def run_gpu(case, atomic=False):
+    eq = eqlb.FluxEqlbSE(case.k, case.mesh, case.F, case.G, degree_proj=case.T.p, atomic=atomic)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    eq.equilibrate_fluxes()
+    return eq
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("kind,n,scramble", [("crossed", 4, None), ("crossed", 5, 3), ("randdiag", 6, 2)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_patch_maps_bit_exact(kind, n, scramble, k):
+    from oracle import pyoracle as po
+
+    m = make_mesh(kind, n, scramble, perturb=0.2)
+    case = PoissonCase(m, k, [[1, 4], [1, 3], [2], [1, 3, 4]], seed=5, galerkin=False)
+    ref = po.se_patch_maps(m, case.T, case.oracle_bc())
+    eq = eqlb.FluxEqlbSE(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    got = eq.problem.patch_maps()
+    for key in INT_KEYS:
+        assert np.array_equal(got[key], ref[key]), key
+    dm = eq.problem.se_dofmaps()
+    for key in ["dofmap", "projflux_fct", "bmarkers"]:
+        assert np.array_equal(dm[key], ref[key]), key
+    # colouring: no two patches of a colour share a cell
+    col = got["colour"]
+    assert (col[m.cell_node[:, 0]] != col[m.cell_node[:, 1]]).all()
+    assert (col[m.cell_node[:, 0]] != col[m.cell_node[:, 2]]).all()
+    assert (col[m.cell_node[:, 1]] != col[m.cell_node[:, 2]]).all()
+
+
+@pytest.mark.parametrize("kind,n,scramble", [("crossed", 4, None), ("crossed", 5, 3), ("randdiag", 6, 2)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("nsets", [[[]], [[1, 4]], [[1, 4], [1, 3], [2], [1, 3, 4]]])
+def test_se_flux_parity(kind, n, scramble, k, nsets):
+    from oracle import pyoracle as po
+
+    m = make_mesh(kind, n, scramble, perturb=0.25)
+    case = PoissonCase(m, k, nsets, seed=7)
+    ref = po.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    eq = run_gpu(case)
+    for r in range(case.nrhs):
+        assert rel_err(eq.list_flux[r], ref[r]) < RTOL
+        # the reference's acceptance invariants hold for the GPU result itself
+        assert fm.check_divergence(m, case.T, eq.list_flux[r], case.G[r], case.F[r]) < 1e-12
+        assert fm.check_jump(m, case.T, eq.list_flux[r], case.G[r]) < 1e-11
+        if len(case.neu[r]):
+            assert fm.check_bc(m, case.T, eq.list_flux[r], case.G[r], case.bdata.bflux[r], case.neu[r]) < 1e-11
+
+
+def test_se_random_data_parity():
+    """Non-Galerkin random data (the benchmark's input distribution): parity with the
+    oracle must hold for any input, closure of the patch fluxes is not required."""
+    from oracle import pyoracle as po
+
+    m = make_mesh("crossed", 8, None)
+    case = PoissonCase(m, 2, [[]], seed=11, galerkin=False)
+    ref = po.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    eq = run_gpu(case)
+    assert rel_err(eq.list_flux[0], ref[0]) < RTOL
+
+
+def test_se_atomic_matches_coloured():
+    m = make_mesh("crossed", 6, 4, perturb=0.2)
+    case = PoissonCase(m, 2, [[1, 4]], seed=3)
+    a = run_gpu(case, atomic=False).list_flux[0]
+    b = run_gpu(case, atomic=True).list_flux[0]
+    assert rel_err(a, b) < 1e-13
+
+
+def test_se_accumulates_like_reference():
+    """Output is += (se/solve_patch_semiexplt.hpp:1159): a second call doubles it."""
+    m = make_mesh("crossed", 4, None)
+    case = PoissonCase(m, 2, [[]], seed=1)
+    eq = run_gpu(case)
+    once = eq.list_flux[0].copy()
+    eq.equilibrate_fluxes()
+    assert rel_err(eq.list_flux[0], 2 * once) < 1e-14
+
+
+def test_lower_degree_data():
+    """degree of projected data below k-1 (reference test matrix
+    test_fluxeqlb_conditions.py:62-64)."""
+    from oracle import pyoracle as po
+
+    m = make_mesh("crossed", 4, 2, perturb=0.2)
+    for k, p in [(2, 0), (3, 1), (3, 0)]:
+        case = PoissonCase(m, k, [[1, 4]], seed=2, p=p)
+        ref = po.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+        eq = run_gpu(case)
+        assert rel_err(eq.list_flux[0], ref[0]) < RTOL
+
+
+def test_errors_like_reference():
+    from dolfinx_eqlb_b200 import mesh as ms
+
+    # "right" diagonal mesh has 1-cell corner patches -> reference throws (se/Patch.cpp:353-359)
+    x = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    m = ms.build_topology(x, np.array([[0, 1, 3], [0, 2, 3]]))
+    with pytest.raises(RuntimeError, match="has only 1 cells"):
+        eqlb.FluxEqlbSE(1, m, [np.zeros(2)], [np.zeros(4)])

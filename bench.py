@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the equilibration hot path: equilibrated patches / second.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--path ev|se] [--n 1024]
+
+One "step" = one equilibrate_fluxes()-equivalent call (all patches of the mesh,
+patch maps resident, inputs resident in HBM).  Workload at N=1: BASELINE.json
+configs[1] (Poisson, flux degree 2, 1024x1024 crossed unit square, pure
+Dirichlet, synthetic random coefficients).  Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20240611
+
+
+def synthetic_inputs(ncell, ndg, nrhs, seed=SEED):
+    """`G ~ +-2(U+0.1)`, `f ~ 2(U+0.1)` (testcase_general.py:118-131)."""
+    rng = np.random.default_rng(seed)
+    G, F = [], []
+    for _ in range(nrhs):
+        g = 2.0 * (rng.random(ncell * ndg * 2) + 0.1)
+        g *= np.where(rng.random(ncell * ndg * 2) < 0.5, -1.0, 1.0)
+        G.append(g)
+        F.append(2.0 * (rng.random(ncell * ndg) + 0.1))
+    return G, F
+
+
+def alg_bytes_per_cell(k, ndg, nrt, nrhs, path):
+    """Compulsory unique HBM traffic per cell: 48 B geometry +
+    nrhs * (16 ndg [G] + 8 ndg [f] + 8 ndofs [sigma out])."""
+    nout = nrt if path == "se" else (k * k - k) + 1.5 * k  # EV: facet dofs shared by 2 cells
+    return 48 + nrhs * (16 * ndg + 8 * ndg + 8 * nout)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_case(n, k, nrhs):
+    from dolfinx_eqlb_b200 import eqlb, mesh as ms, tables as tb
+
+    T = tb.make_tables(k)
+    m = ms.crossed_unit_square(n)
+    G, F = synthetic_inputs(m.ncell, T.ndg, nrhs)
+    bfct = [m.boundary_facets([1, 2, 3, 4]) for _ in range(nrhs)]
+    bcs = [[] for _ in range(nrhs)]
+    return m, T, G, F, bfct, bcs
+
+
+def time_oracle(path, n, k, nrhs, repeats):
+    """CPU baseline: the oracle restatement (reference loop structure, 1 thread) on a
+    bounded sample of the same workload; min over repeats like perftest.py:39-40."""
+    from oracle import pyoracle as po
+    from dolfinx_eqlb_b200 import mesh as ms
+
+    m, T, G, F, bfct, bcs = build_case(n, k, nrhs)
+    ft = np.stack([ms.facet_types(m, [1, 2, 3, 4], []) for _ in range(nrhs)])
+    bc = po.BCData(ft)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if path == "se":
+            po.se_run(m, T, bc, G, F)
+        else:
+            po.ev_run(m, T, bc, G, F)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return m.nnode / best, m.nnode, best
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm (oracle port; the reference
+    itself cannot be built here - SURVEY 8c) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = args.cpu_n
+    vals = []
+    for _ in range(max(args.warmup, 0)):
+        time_oracle(args.path, n_sample, args.k, args.nrhs, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, npatch, dt = time_oracle(args.path, n_sample, args.k, args.nrhs, 1)
+        vals.append((v, dt))
+    total = time.perf_counter() - t0
+    value = float(np.mean([v for v, _ in vals]))
+    ms_step = 1e3 * float(np.mean([d for _, d in vals]))
+    sample = f"crossed {n_sample}x{n_sample} ({npatch} patches) of the {args.n}x{args.n} workload, 1 thread, mean of {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": total,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    name = {"ev": "Poisson FluxEqlbEV, P2 primal / RT2 flux", "se": "Poisson FluxEqlbSE"}[args.path]
+    return {
+        "workload": f"{name}, degree_flux={args.k}, {args.n}x{args.n} crossed unit square, pure Dirichlet, nrhs={args.nrhs}",
+        "path": args.path, "degree_flux": args.k, "n": args.n, "nrhs": args.nrhs,
+        "l2": "inputs larger than L2 (no flush needed)", "accumulation": "colour-ordered (deterministic)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--path", default=os.environ.get("EQLB_BENCH_PATH", "se"), choices=["se", "ev"])
+    ap.add_argument("--k", type=int, default=2)
+    ap.add_argument("--nrhs", type=int, default=1)
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--cpu-n", type=int, default=256, dest="cpu_n")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+
+    from dolfinx_eqlb_b200 import cabi, eqlb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- problem setup (not timed): mesh, tables, device residency, patch maps ----
+    m, T, G, F, bfct, bcs = build_case(args.n, args.k, args.nrhs)
+    k, nrhs = args.k, args.nrhs
+    if args.path == "se":
+        eq = eqlb.FluxEqlbSE(k, m, F, G)
+        nout = m.ncell * T.nrt
+    else:
+        eq = eqlb.FluxEqlbEV(k, m, F, G)
+        nout = eq.ndofs
+    eq.set_boundary_conditions(bfct, bcs)
+    prob = eq.problem
+    lib = prob.lib
+    stream = torch.cuda.current_stream()
+    prob.set_stream(stream.cuda_stream)
+
+    dG = [torch.from_numpy(g).cuda() for g in G]
+    dF = [torch.from_numpy(f).cuda() for f in F]
+    dS = [torch.zeros(nout, dtype=torch.float64, device="cuda") for _ in range(nrhs)]
+
+    def dptrs(ts):
+        arr = (cabi.c_double_p * len(ts))()
+        for i, t in enumerate(ts):
+            arr[i] = C.cast(t.data_ptr(), cabi.c_double_p)
+        return arr
+
+    pG, pF, pS = dptrs(dG), dptrs(dF), dptrs(dS)
+
+    def step_device():
+        if args.path == "se":
+            rc = lib.eqlb_se_run(prob.h, pG, pF, pS, cabi.c_double_p(), 1)
+        else:
+            rc = lib.eqlb_ev_run(prob.h, pG, pF, pS, 1)
+        if rc != 0:
+            raise RuntimeError(lib.eqlb_last_error().decode())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = prob.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    launches = prob.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    npatch_total = m.nnode * world
+    value = npatch_total / (ms_step * 1e-3)
+
+    # ---- end-to-end through the host API: pinned host buffers, H2D + D2H inside ----
+    hG = [torch.from_numpy(g).pin_memory() for g in G]
+    hF = [torch.from_numpy(f).pin_memory() for f in F]
+    hS = [torch.zeros(nout, dtype=torch.float64).pin_memory() for _ in range(nrhs)]
+    qG, qF, qS = dptrs(hG), dptrs(hF), dptrs(hS)
+
+    def step_host():
+        if args.path == "se":
+            rc = lib.eqlb_se_run(prob.h, qG, qF, qS, cabi.c_double_p(), 0)
+        else:
+            rc = lib.eqlb_ev_run(prob.h, qG, qF, qS, 0)
+        if rc != 0:
+            raise RuntimeError(lib.eqlb_last_error().decode())
+
+    e2e_steps = max(3, min(args.steps, 5))
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF) + sum(s.numel() * 8 for s in hS)
+    d2h = sum(s.numel() * 8 for s in hS)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (the patch kernel is the whole step) ----
+    peak, peak_src = peaks()
+    bpc = alg_bytes_per_cell(k, T.ndg, T.nrt, nrhs, args.path)
+    alg_bytes_step = bpc * m.ncell  # per rank
+    achieved = alg_bytes_step / (ms_step * 1e-3) / 1e9
+    roof = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "se_patch_kernel" if args.path == "se" else "ev_patch_kernel",
+        "alg_bytes_per_patch": bpc * m.ncell / m.nnode, "peak_source": peak_src,
+        "launches_per_step": launches / args.steps,
+    }
+    cpu = None
+    if not args.no_cpu:
+        v, npatch_s, dt = time_oracle(args.path, args.cpu_n, k, nrhs, 3)
+        cpu = {"value": v, "unit": "patches/s", "cores": 1, "kind": "port",
+               "sample": f"crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches) of the same workload, min of 3, {os.cpu_count()} host cores present"}
+    line = {
+        "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+        "e2e": {"value": npatch_total / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

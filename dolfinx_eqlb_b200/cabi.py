@@ -46,7 +46,7 @@ class EqlbMesh(C.Structure):
 
 _TABLE_DOUBLES = ["qpts", "qwts", "fpts_s", "fwts", "M", "rt_q", "rt_f", "dg_q", "dg_f", "hat_q", "hat_f", "trafo"]
 _TABLE_INTS = ["fct_closure", "div_lm"]
-_TABLE_REF = ["rt_mass", "fct_mom", "cell_mom_f", "cell_mom_g", "bc_mat", "rt_p1"]
+_TABLE_REF = ["rt_mass", "fct_mom", "cell_mom_f", "cell_mom_g", "bc_mat", "rt_p1", "dg_mono", "hat_dg_rt", "mono_int"]
 
 
 class EqlbTables(C.Structure):

@@ -197,6 +197,9 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         append(flat, t->bc_mat, (size_t)9 * k * k, tv.o_bc_mat);
         append(flat, t->trafo, (size_t)k * k, tv.o_trafo);
         append(flat, t->rt_p1, (size_t)nrt * 6, tv.o_rt_p1);
+        append(flat, t->dg_mono, (size_t)nt * ndg, tv.o_dg_mono);
+        append(flat, t->hat_dg_rt, (size_t)3 * ndg * nrt * 2, tv.o_hat_dg_rt);
+        append(flat, t->mono_int, (size_t)nt, tv.o_mono_int);
         h->d_tables.upload(flat.data(), flat.size());
         tv.data = h->d_tables.p;
         tv.ndoubles = (int)flat.size();

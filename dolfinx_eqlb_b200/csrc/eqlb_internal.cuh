@@ -100,6 +100,9 @@ struct TableView
   int o_bc_mat;      // [3][3][k][k]
   int o_trafo;       // [k][k]
   int o_rt_p1;       // [nrt][2][3]
+  int o_dg_mono;     // [1+ndiv][ndg]
+  int o_hat_dg_rt;   // [3][ndg][nrt][2]
+  int o_mono_int;    // [1+ndiv]
 };
 
 // Mesh connectivity on the device (patch builder input)
@@ -116,7 +119,8 @@ struct MeshView
 // SoA with the patch index fastest so that a warp of consecutive patches loads
 // coalesced.  info byte per (cell slot a, patch): bits 0-1 local id of the patch
 // node in T_a, bits 2-3 local facet id of E_{a-1} in T_a, bits 4-5 local facet id of
-// E_a in T_a, bit 6 reversed(a,0), bit 7 reversed(a,1).
+// E_a in T_a, bit 6 reversed(a,0), bit 7 reversed(a,1), bit 8/9 facet-reflection bit
+// (fct_perms) of E_{a-1} / E_a in T_a.
 // rhs byte per (rhs, patch): bits 0-1 patch type, bit 2 reversion_required,
 // bit 3 E_0 carries a flux BC, bit 4 E_n carries a flux BC.
 struct PatchView
@@ -128,7 +132,7 @@ struct PatchView
   const int32_t* node;   // [stride]     patch-central node
   const uint8_t* ncells; // [stride]
   const int32_t* cell;   // [ncmax][stride]
-  const uint8_t* info;   // [ncmax][stride]
+  const uint16_t* info;  // [ncmax][stride]
   const uint8_t* rhsinfo; // [nrhs][stride]
 };
 
@@ -176,7 +180,8 @@ struct eqlb_handle
   int ncolours = 0;
   size_t pstride = 0;
   DevBuf<int32_t> d_pnode, d_pcell;
-  DevBuf<uint8_t> d_pncells, d_pinfo, d_prhs;
+  DevBuf<uint8_t> d_pncells, d_prhs;
+  DevBuf<uint16_t> d_pinfo;
 
   // staging buffers for host-pointer calls
   DevBuf<double> d_stage_G, d_stage_f, d_stage_sigma, d_stage_korn;

@@ -183,7 +183,7 @@ __global__ void patch_builder_kernel(MeshView m, const int8_t* __restrict__ face
                                      const int32_t* __restrict__ order, int npatch, size_t stride, int ncmax,
                                      // compact records (colour order)
                                      int32_t* __restrict__ pnode, uint8_t* __restrict__ pncells,
-                                     int32_t* __restrict__ pcell, uint8_t* __restrict__ pinfo,
+                                     int32_t* __restrict__ pcell, uint16_t* __restrict__ pinfo,
                                      uint8_t* __restrict__ prhs,
                                      // expanded, reference layout (node order); may be null
                                      int32_t* __restrict__ x_ncells, int32_t* __restrict__ x_cells,
@@ -212,8 +212,10 @@ __global__ void patch_builder_kernel(MeshView m, const int8_t* __restrict__ face
     if (pcell)
     {
       pcell[(size_t)(a - 1) * stride + i] = F.cells[a];
-      pinfo[(size_t)(a - 1) * stride + i]
-          = (uint8_t)(F.inod[a] | (F.fl[2 * a - 1] << 2) | (F.fl[2 * a] << 4) | (r0 ? 64 : 0) | (r1 ? 128 : 0));
+      const int rho_m = m.fct_perms[3 * F.cells[a] + F.fl[2 * a - 1]] ? 256 : 0;
+      const int rho_p = m.fct_perms[3 * F.cells[a] + F.fl[2 * a]] ? 512 : 0;
+      pinfo[(size_t)(a - 1) * stride + i] = (uint16_t)(F.inod[a] | (F.fl[2 * a - 1] << 2) | (F.fl[2 * a] << 4)
+                                                       | (r0 ? 64 : 0) | (r1 ? 128 : 0) | rho_m | rho_p);
     }
     if (x_rev)
     {

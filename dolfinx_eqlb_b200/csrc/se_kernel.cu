@@ -38,11 +38,17 @@ struct SeDims
 // packed lower-triangular index
 __device__ __forceinline__ int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <int K, int NDG, int NCMAX>
+// EV = false: semi-explicit equilibration (corrector sigma_eq, DRT output)
+// EV = true : constrained minimisation of FluxEqlbEV solved by the null-space method:
+//             explicit conforming particular solution with div = Pi(hat f + grad(hat).G)
+//             (+ the mean-value shift the reference's Lagrange multiplier produces),
+//             then || sigma_p + Z u - hat G || -> min over the same patch-wise H(div=0)
+//             basis Z; output into the conforming hierarchic RT vector.
+template <int K, int NDG, int NCMAX, bool EV>
 __global__ void __launch_bounds__(128)
-se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __restrict__ cellJ,
-                const int32_t* __restrict__ dgmap, int nrhs, RhsPtrs ptrs,
-                const double* __restrict__ bflux, size_t bflux_stride, int use_atomics)
+patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __restrict__ cellJ,
+             const int32_t* __restrict__ dgmap, int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux,
+             size_t bflux_stride, int use_atomics, const int32_t* __restrict__ cell_fct, int nfct)
 {
   using D = SeDims<K>;
   constexpr int k = K, ndiv = D::ndiv, nadd = D::nadd, nrt = D::nrt, nact = D::nact, ncol = D::ncol, nz = D::nz;
@@ -59,6 +65,9 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
   const double* __restrict__ t_cmg = s_tab + tv.o_cell_mom_g;  // [3][NT][NDG][2]
   const double* __restrict__ t_bc = s_tab + tv.o_bc_mat;       // [3][3][k][k]
   const double* __restrict__ t_trafo = s_tab + tv.o_trafo;     // [k][k]
+  const double* __restrict__ t_dgm = s_tab + tv.o_dg_mono;     // [NT][NDG]
+  const double* __restrict__ t_hdr = s_tab + tv.o_hat_dg_rt;   // [3][NDG][nrt][2]
+  const double* __restrict__ t_mono = s_tab + tv.o_mono_int;   // [NT]
 
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= count)
@@ -68,7 +77,7 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
 
   // ---- per-cell geometry / orientation (independent of the RHS) ----
   int32_t cell[NCMAX];
-  uint8_t info[NCMAX];
+  uint16_t info[NCMAX];
   double gm[NCMAX][3];   // J^T J / |detJ|
   double adj[NCMAX][4];  // adj(J) = detJ * K
   double detJ[NCMAX];
@@ -78,7 +87,7 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
   {
     const int32_t c = pv.cell[(size_t)a * pv.stride + ip];
     cell[a] = c;
-    const uint8_t inf = pv.info[(size_t)a * pv.stride + ip];
+    const uint16_t inf = pv.info[(size_t)a * pv.stride + ip];
     info[a] = inf;
     const double2 j0 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c];
     const double2 j1 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c + 1];
@@ -142,28 +151,82 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
       const double* wp = t_fmom + ((fp * 3 + v) * k) * NDG;
       const double* cf_ = t_cmf + (v * NT) * NDG;
       const double* cg_ = t_cmg + (v * NT) * NDG * 2;
+      // EV: reference gradient of the hat function of local vertex v
+      const double ghx = (v == 0) ? -1.0 : (v == 1 ? 1.0 : 0.0);
+      const double ghy = (v == 0) ? -1.0 : (v == 2 ? 1.0 : 0.0);
 #pragma unroll
       for (int i = 0; i < NDG; ++i)
       {
         const size_t dof = dgmap ? (size_t)dgmap[(size_t)c * NDG + i] : (size_t)c * NDG + i;
         const double2 g = reinterpret_cast<const double2*>(G)[dof];
         const double fi = Fv[dof];
-        const double gnm = nmx * g.x + nmy * g.y;
-        const double gnp = npx * g.x + npy * g.y;
         // adj^T applied to reference gradients: d/dx_phys * detJ
         const double a0 = ad[0] * g.x + ad[1] * g.y;  // multiplies d/dxhat
         const double a1 = ad[2] * g.x + ad[3] * g.y;  // multiplies d/dyhat
         const double fd = detJ[a] * fi;
-#pragma unroll
-        for (int j = 0; j < k; ++j)
+        if (EV)
         {
-          mm[a][j] += wm[j * NDG + i] * gnm;
-          mp[a][j] += wp[j * NDG + i] * gnp;
+          // detJ * (hat f + grad(hat).G) tested with x^l y^m
+          const double gg = a0 * ghx + a1 * ghy;
+#pragma unroll
+          for (int t = 0; t < NT; ++t)
+            cm[a][t] += fd * cf_[t * NDG + i] + gg * t_dgm[t * NDG + i];
         }
+        else
+        {
+          const double gnm = nmx * g.x + nmy * g.y;
+          const double gnp = npx * g.x + npy * g.y;
+#pragma unroll
+          for (int j = 0; j < k; ++j)
+          {
+            mm[a][j] += wm[j * NDG + i] * gnm;
+            mp[a][j] += wp[j * NDG + i] * gnp;
+          }
+#pragma unroll
+          for (int t = 0; t < NT; ++t)
+            cm[a][t] += fd * cf_[t * NDG + i] - a0 * cg_[(t * NDG + i) * 2] - a1 * cg_[(t * NDG + i) * 2 + 1];
+        }
+      }
+    }
+    if (EV && (ptype == EQLB_PATCH_INTERNAL || ptype == EQLB_PATCH_ESSNT_DUAL))
+    {
+      // mean-value shift: the KKT system of the reference carries a Lagrange multiplier
+      // on the DG block (ev/assembly.hpp:283-298) which shifts the divergence data by a
+      // patch constant so that it is compatible with the prescribed boundary fluxes
+      double tot = 0.0, area2 = 0.0;
+      for (int a = 0; a < nc; ++a)
+      {
+        tot += (detJ[a] > 0.0 ? cm[a][0] : -cm[a][0]);
+        area2 += fabs(detJ[a]);
+      }
+      if (ptype == EQLB_PATCH_ESSNT_DUAL)
+      {
+        for (int e = 0; e < 2; ++e)
+        {
+          const int a = e ? nc - 1 : 0;
+          const int v = info[a] & 3;
+          const int fb = e ? (info[a] >> 4) & 3 : (info[a] >> 2) & 3;
+          const double* bsrc = bflux + (size_t)r * bflux_stride + (size_t)cell[a] * nrt + fb * k;
+          int nzero = 0;
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+          {
+            const double bi = bsrc[i];
+            if (fabs(bi) < 1e-7)
+              ++nzero;
+            s += t_bc[((fb * 3 + v) * k) * k + i] * bi;
+          }
+          if (nzero < k)
+            tot -= (e ? pp[a] : pm[a]) * s;
+        }
+      }
+      const double lam = tot / (0.5 * area2);
+#pragma unroll 1
+      for (int a = 0; a < nc; ++a)
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-          cm[a][t] += fd * cf_[t * NDG + i] - a0 * cg_[(t * NDG + i) * 2] - a1 * cg_[(t * NDG + i) * 2 + 1];
-      }
+          cm[a][t] -= lam * detJ[a] * t_mono[t];
     }
 
     // ---- step 1: explicit sweep ----
@@ -408,6 +471,29 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
           s += MB[q][c2] * cf[a][c2];
         y[q] = s;
       }
+      if (EV)
+      {
+        // y -= (hat G, phi_q)_T = sgn * sum_m (J^T G_m) . H[v][m][rdof(q)]
+        const int v = info[a] & 3;
+        const double sgn = detJ[a] > 0.0 ? 1.0 : -1.0;
+        const double* ad = adj[a];
+#pragma unroll
+        for (int mI = 0; mI < NDG; ++mI)
+        {
+          const size_t dof = dgmap ? (size_t)dgmap[(size_t)cell[a] * NDG + mI] : (size_t)cell[a] * NDG + mI;
+          const double2 g = reinterpret_cast<const double2*>(G)[dof];
+          // J = [[adj3, -adj1], [-adj2, adj0]]
+          const double jg0 = sgn * (ad[3] * g.x - ad[2] * g.y);
+          const double jg1 = sgn * (-ad[1] * g.x + ad[0] * g.y);
+          const double* hh = t_hdr + ((size_t)(v * NDG + mI) * nrt) * 2;
+#pragma unroll
+          for (int q = 0; q < nact; ++q)
+          {
+            const int rq = rdof(q);
+            y[q] -= jg0 * hh[rq * 2] + jg1 * hh[rq * 2 + 1];
+          }
+        }
+      }
       // reversed E_{a-1}: transform the test/trial functions of that facet
       if (rev0)
       {
@@ -600,6 +686,64 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
         for (int i = 0; i < k; ++i)
           um[i] = tmp[i];
       }
+      if (EV)
+      {
+        // conforming hierarchic RT vector: [fct*k + j] facet dofs in the global (low ->
+        // high vertex) orientation, then [nfct*k + cell*(k*k-k) + i] cell dofs.
+        // T_a owns facet E_a; T_1 of a boundary patch also owns E_0.
+        constexpr int ncd = k * k - k;
+        const int32_t c = cell[a];
+        for (int side = (a == 0 && !internal) ? 0 : 1; side < 2; ++side)
+        {
+          const int fl = side ? fp : fm;
+          const bool refl = (info[a] & (side ? 512 : 256)) != 0;
+          const int32_t fg = cell_fct[3 * (size_t)c + fl];
+          double cl[K], cg[K];
+#pragma unroll
+          for (int j = 0; j < k; ++j)
+            cl[j] = side ? (cf[a][k + j] + up[j]) : (cf[a][j] + um[j]);
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+          {
+            double acc = cl[i];
+            if (refl)
+            {
+              acc = 0.0;
+#pragma unroll
+              for (int j = 0; j < k; ++j)
+                acc += t_trafo[j * k + i] * cl[j];
+            }
+            cg[i] = acc;
+          }
+#pragma unroll
+          for (int i = 0; i < k; ++i)
+          {
+            if (use_atomics)
+              atomicAdd(sig + (size_t)fg * k + i, cg[i]);
+            else
+              sig[(size_t)fg * k + i] += cg[i];
+          }
+        }
+        double* dstc = sig + (size_t)nfct * k + (size_t)c * ncd;
+#pragma unroll
+        for (int t = 0; t < ndiv; ++t)
+        {
+          if (use_atomics)
+            atomicAdd(dstc + t, cf[a][2 * k + nadd + t]);
+          else
+            dstc[t] += cf[a][2 * k + nadd + t];
+        }
+#pragma unroll
+        for (int i = 0; i < nadd; ++i)
+        {
+          const double val = cf[a][2 * k + i] + L[nf * (k - 1) + 1 + a * nadd + i];
+          if (use_atomics)
+            atomicAdd(dstc + ndiv + i, val);
+          else
+            dstc[ndiv + i] += val;
+        }
+        continue;
+      }
       double* dst = sig + (size_t)cell[a] * nrt;
       if (use_atomics)
       {
@@ -635,8 +779,8 @@ se_patch_kernel(PatchView pv, int first, int count, TableView tv, const double* 
   }
 }
 
-template <int K, int NDG>
-void launch_se_t(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
+template <int K, int NDG, bool EV>
+void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
 {
   RhsPtrs ptrs;
   for (int r = 0; r < h->nrhs; ++r)
@@ -649,8 +793,8 @@ void launch_se_t(eqlb_handle* h, const double* const* dG, const double* const* d
   const int bs = 128;
   const size_t smem = (size_t)h->tv.ndoubles * sizeof(double);
   const bool atomics = (h->flags & EQLB_FLAG_ATOMIC) != 0;
-  auto kern8 = se_patch_kernel<K, NDG, 8>;
-  auto kern16 = se_patch_kernel<K, NDG, EQLB_NCMAX>;
+  auto kern8 = patch_kernel<K, NDG, 8, EV>;
+  auto kern16 = patch_kernel<K, NDG, EQLB_NCMAX, EV>;
   auto kern = (h->ncmax <= 8) ? kern8 : kern16;
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int32_t* dgmap = h->dg_identity ? nullptr : h->d_dg_dofmap.p;
@@ -659,7 +803,7 @@ void launch_se_t(eqlb_handle* h, const double* const* dG, const double* const* d
   {
     const int count = h->nnode;
     kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, 0, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
-                                                        h->d_bflux.p, bstride, 1);
+                                                        h->d_bflux.p, bstride, 1, h->d_cell_fct.p, h->nfct);
     CUDA_CHECK(cudaGetLastError());
     h->launches++;
   }
@@ -672,10 +816,42 @@ void launch_se_t(eqlb_handle* h, const double* const* dG, const double* const* d
       if (count == 0)
         continue;
       kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, first, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
-                                                          h->d_bflux.p, bstride, 0);
+                                                          h->d_bflux.p, bstride, 0, h->d_cell_fct.p, h->nfct);
       CUDA_CHECK(cudaGetLastError());
       h->launches++;
     }
+  }
+}
+
+template <bool EV>
+void dispatch(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
+{
+  const int key = h->k * 100 + h->ndg;
+  switch (key)
+  {
+  case 101:
+    launch_patch_t<1, 1, EV>(h, dG, dF, dSigma);
+    break;
+  case 201:
+    launch_patch_t<2, 1, EV>(h, dG, dF, dSigma);
+    break;
+  case 203:
+    launch_patch_t<2, 3, EV>(h, dG, dF, dSigma);
+    break;
+  case 301:
+    launch_patch_t<3, 1, EV>(h, dG, dF, dSigma);
+    break;
+  case 303:
+    launch_patch_t<3, 3, EV>(h, dG, dF, dSigma);
+    break;
+  case 306:
+    launch_patch_t<3, 6, EV>(h, dG, dF, dSigma);
+    break;
+  case 410:
+    launch_patch_t<4, 10, EV>(h, dG, dF, dSigma);
+    break;
+  default:
+    throw EqlbError(EQLB_ERR_INPUT, "patch kernel: unsupported (degree_flux, degree_dg) combination");
   }
 }
 
@@ -684,31 +860,10 @@ void launch_se_t(eqlb_handle* h, const double* const* dG, const double* const* d
 void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn)
 {
   (void)dKorn;
-  const int key = h->k * 100 + h->ndg;
-  switch (key)
-  {
-  case 101:
-    launch_se_t<1, 1>(h, dG, dF, dSigma);
-    break;
-  case 201:
-    launch_se_t<2, 1>(h, dG, dF, dSigma);
-    break;
-  case 203:
-    launch_se_t<2, 3>(h, dG, dF, dSigma);
-    break;
-  case 301:
-    launch_se_t<3, 1>(h, dG, dF, dSigma);
-    break;
-  case 303:
-    launch_se_t<3, 3>(h, dG, dF, dSigma);
-    break;
-  case 306:
-    launch_se_t<3, 6>(h, dG, dF, dSigma);
-    break;
-  case 410:
-    launch_se_t<4, 10>(h, dG, dF, dSigma);
-    break;
-  default:
-    throw EqlbError(EQLB_ERR_INPUT, "SE kernel: unsupported (degree_flux, degree_dg) combination");
-  }
+  dispatch<false>(h, dG, dF, dSigma);
+}
+
+void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
+{
+  dispatch<true>(h, dG, dF, dSigma);
 }

@@ -335,6 +335,10 @@ class Tables:
     bc_mat: np.ndarray = None  # [3 f][3 v][k j][k i]   int s^j (phi_{f,i}.n_f) lam_v ds
     # weak symmetry (stress) reference matrices
     rt_p1: np.ndarray = None  # [nrt][2][3]  int phi_i^d lam_v
+    # constrained minimisation (EV) reference matrices
+    dg_mono: np.ndarray = None  # [1+ndiv][ndg]       int psi_i x^l y^m
+    hat_dg_rt: np.ndarray = None  # [3 v][ndg][nrt][2]  int lam_v psi_m phi_i^d
+    mono_int: np.ndarray = None  # [1+ndiv]            int x^l y^m
     extra: dict = field(default_factory=dict)
 
 
@@ -470,6 +474,22 @@ def make_tables(k: int, p: int | None = None) -> Tables:
             for v in range(3):
                 rp[i, d, v] = float(p_int_cell(p_mul(rt[i][d], HAT[v])))
     T.rt_p1 = rp
+
+    dgm = np.zeros((1 + ndiv, ndg))
+    mono = np.zeros(1 + ndiv)
+    for t, (l, m) in enumerate(lm_all):
+        mono[t] = float(p_int_cell({(l, m): Fr(1)}))
+        for i, ph in enumerate(dg):
+            dgm[t, i] = float(p_int_cell(p_mul(ph, {(l, m): Fr(1)})))
+    T.dg_mono, T.mono_int = dgm, mono
+    hdr = np.zeros((3, ndg, nrt, 2))
+    for v in range(3):
+        for m_, ph in enumerate(dg):
+            w = p_mul(HAT[v], ph)
+            for i in range(nrt):
+                hdr[v, m_, i, 0] = float(p_int_cell(p_mul(w, rt[i][0])))
+                hdr[v, m_, i, 1] = float(p_int_cell(p_mul(w, rt[i][1])))
+    T.hat_dg_rt = hdr
 
     T.extra["rt_exact"] = rt
     T.extra["dg_exact"] = dg

@@ -77,6 +77,7 @@ typedef struct eqlb_tables {
   const int32_t *fct_closure, *div_lm;
   /* reference-matrix tables (exact integrals on the reference cell) */
   const double *rt_mass, *fct_mom, *cell_mom_f, *cell_mom_g, *bc_mat, *rt_p1;
+  const double *dg_mono, *hat_dg_rt, *mono_int; /* EV load vector / divergence data */
 } eqlb_tables;
 
 typedef struct eqlb_handle eqlb_handle;

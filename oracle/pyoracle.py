@@ -55,6 +55,16 @@ def lib():
             C.POINTER(EqlbMesh), C.POINTER(EqlbTables), C.c_int, c_int8_p, c_int8_p, C.c_int, C.c_int,
             c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int8_p, c_int8_p, c_uint8_p, c_uint8_p, c_int32_p, c_int32_p, c_int8_p,
         ]
+        L.oracle_ev_run.restype = C.c_int
+        L.oracle_ev_run.argtypes = [
+            C.POINTER(EqlbMesh), C.POINTER(EqlbTables), C.c_int, c_int8_p, C.POINTER(c_double_p),
+            C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p),
+        ]
+        L.oracle_ev_patch_maps.restype = C.c_int
+        L.oracle_ev_patch_maps.argtypes = [
+            C.POINTER(EqlbMesh), C.POINTER(EqlbTables), C.c_int, c_int8_p, C.c_int,
+            c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+        ]
         _lib = L
     return _lib
 
@@ -132,4 +142,50 @@ def se_patch_maps(mesh, tables, bc: BCData, stress=False):
     )
     _check(rc)
     out["ncmax"] = ncmax
+    return out
+
+
+def ev_ndofs(mesh, tables):
+    k = tables.k
+    return mesh.nfct * k + mesh.ncell * (k * k - k)
+
+
+def ev_run(mesh, tables, bc: BCData, G, F, sigma0=None):
+    """oracle of `reconstruct_fluxes_minimisation` -> conforming hierarchic-RT vectors."""
+    pm, pt = PackedMesh(mesh, tables.ndg), PackedTables(tables)
+    nrhs = bc.nrhs
+    G = [np.ascontiguousarray(g, dtype=np.float64) for g in G]
+    F = [np.ascontiguousarray(f, dtype=np.float64) for f in F]
+    n = ev_ndofs(mesh, tables)
+    sig = [np.zeros(n) if sigma0 is None else np.array(sigma0[i], dtype=np.float64) for i in range(nrhs)]
+    rc = lib().oracle_ev_run(
+        C.byref(pm.struct), C.byref(pt.struct), nrhs, _i8(bc.facet_type), ptr_array(bc.bflux), ptr_array(G), ptr_array(F),
+        ptr_array(sig),
+    )
+    _check(rc)
+    return sig
+
+
+def ev_patch_maps(mesh, tables, bc: BCData, node):
+    pm, pt = PackedMesh(mesh, tables.ndg), PackedTables(tables)
+    ncmax = int(np.diff(mesh.node_cell_off).max())
+    k = tables.k
+    nz = tables.nrt + tables.ndg - k
+    nc = np.zeros(1, np.int32)
+    out = dict(
+        cells=np.full(ncmax, -1, np.int32), fcts=np.full(ncmax + 1, -1, np.int32), inodes_local=np.full(ncmax, -1, np.int8),
+        dofs_elmt=np.full(ncmax * nz, -1, np.int32), dofs_patch=np.full(ncmax * nz, -1, np.int32),
+        dofs_global=np.full(ncmax * nz, -1, np.int32),
+        list_patch=np.full(ncmax * (k * k - k) + (ncmax + 1) * k, -1, np.int32),
+        list_global=np.full(ncmax * (k * k - k) + (ncmax + 1) * k, -1, np.int32),
+    )
+    rc = lib().oracle_ev_patch_maps(
+        C.byref(pm.struct), C.byref(pt.struct), bc.nrhs, _i8(bc.facet_type), int(node), nc.ctypes.data_as(c_int32_p),
+        out["cells"].ctypes.data_as(c_int32_p), out["fcts"].ctypes.data_as(c_int32_p), _i8(out["inodes_local"]),
+        out["dofs_elmt"].ctypes.data_as(c_int32_p), out["dofs_patch"].ctypes.data_as(c_int32_p),
+        out["dofs_global"].ctypes.data_as(c_int32_p), out["list_patch"].ctypes.data_as(c_int32_p),
+        out["list_global"].ctypes.data_as(c_int32_p),
+    )
+    _check(rc)
+    out["ncells"] = int(nc[0])
     return out

@@ -231,3 +231,19 @@ def check_bc(mesh, T, sigma, G, bflux, neumann):
 def random_dg(rng, n):
     """`2*(U[0,1)+0.1)` like `python/test/unit/testcase_general.py:118-131`."""
     return 2.0 * (rng.random(n) + 0.1)
+
+
+def conforming_to_drt(mesh, T, sig_g):
+    """Conforming hierarchic-RT vector ([fct*k+j][nfct*k + cell*(k^2-k)+i]) -> cell-local
+    DRT coefficients: c_loc = R^T c_glob on reflected facets."""
+    k, nrt = T.k, T.nrt
+    ncd = k * k - k
+    out = np.zeros((mesh.ncell, nrt))
+    R = T.trafo
+    for f in range(3):
+        cg = sig_g[: mesh.nfct * k].reshape(mesh.nfct, k)[mesh.cell_fct[:, f]]
+        refl = mesh.fct_perms.reshape(-1, 3)[:, f].astype(bool)
+        out[:, f * k : (f + 1) * k] = np.where(refl[:, None], cg @ R, cg)
+    if ncd:
+        out[:, 3 * k :] = sig_g[mesh.nfct * k :].reshape(mesh.ncell, ncd)
+    return out.reshape(-1)

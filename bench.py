@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--path", default=os.environ.get("EQLB_BENCH_PATH", "se"), choices=["se", "ev"])
+    ap.add_argument("--path", default=os.environ.get("EQLB_BENCH_PATH", "ev"), choices=["se", "ev"])
     ap.add_argument("--k", type=int, default=2)
     ap.add_argument("--nrhs", type=int, default=1)
     ap.add_argument("--n", type=int, default=1024)

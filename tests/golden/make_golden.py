@@ -1,0 +1,63 @@
+"""Generates tests/golden/*.npz.  The reference ships no golden vectors and
+cannot be imported here, so the vectors are produced by the oracle from seeded inputs
+on the reference's own fixture sizes (2x2 / 5x5 crossed unit squares,
+test_fluxeqlb_conditions.py:47-49) and accepted only if the reference's acceptance
+invariants hold.  Run from the repo root:  python tests/golden/make_golden.py"""
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fem_mini as fm  # noqa: E402
+from common import PoissonCase, make_mesh  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+CASES = [
+    # name, path, kind, n, scramble, perturb, k, neumann sets, seed
+    ("se_k1_crossed2", "se", "crossed", 2, None, 0.0, 1, [[1, 4]], 1),
+    ("se_k2_crossed5_scr", "se", "crossed", 5, 3, 0.2, 2, [[1, 4], [1, 3], [2], [1, 3, 4]], 2),
+    ("se_k3_crossed2", "se", "crossed", 2, 7, 0.1, 3, [[1, 4]], 3),
+    ("ev_k2_crossed5_scr", "ev", "crossed", 5, 3, 0.2, 2, [[], [1, 4]], 4),
+    ("ev_k3_crossed2", "ev", "crossed", 2, None, 0.0, 3, [[]], 5),
+]
+
+
+def build(name, path, kind, n, scramble, perturb, k, nsets, seed):
+    m = make_mesh(kind, n, scramble, perturb)
+    case = PoissonCase(m, k, nsets, seed=seed, hom=(path == "ev"))
+    return m, case
+
+
+def main():
+    out = os.path.dirname(os.path.abspath(__file__))
+    for spec in CASES:
+        name, path = spec[0], spec[1]
+        m, case = build(*spec)
+        if path == "se":
+            sig = po.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+            for r in range(case.nrhs):
+                assert fm.check_divergence(m, case.T, sig[r], case.G[r], case.F[r]) < 1e-12
+                assert fm.check_jump(m, case.T, sig[r], case.G[r]) < 1e-12
+        else:
+            sig = po.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
+            for r in range(case.nrhs):
+                s = fm.conforming_to_drt(m, case.T, sig[r])
+                z = np.zeros_like(case.G[r])
+                assert fm.check_divergence(m, case.T, s, z, case.F[r]) < 1e-10
+                assert fm.check_jump(m, case.T, s, z) < 1e-12
+        maps = po.se_patch_maps(m, case.T, case.oracle_bc())
+        np.savez_compressed(
+            os.path.join(out, name + ".npz"), G=np.array(case.G), F=np.array(case.F), sigma=np.array(sig),
+            cells=maps["cells"], fcts=maps["fcts"], type=maps["type"], fcts_local=maps["fcts_local"],
+            reversed=maps["reversed"], cell_node=m.cell_node, x=m.x,
+        )
+        print("wrote", name)
+
+
+if __name__ == "__main__":
+    main()

@@ -155,6 +155,7 @@ def workload_config(args):
         "workload": f"{name}, degree_flux={args.k}, {args.n}x{args.n} crossed unit square, pure Dirichlet, nrhs={args.nrhs}",
         "path": args.path, "degree_flux": args.k, "n": args.n, "nrhs": args.nrhs,
         "l2": "inputs larger than L2 (no flush needed)", "accumulation": "colour-ordered (deterministic)",
+        "parallelism": "vertex strips, owner-computes patches, NCCL halo sum" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "single GPU",
     }
 
 
@@ -192,13 +193,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- problem setup (not timed): mesh, tables, device residency, patch maps ----
-    m, T, G, F, bfct, bcs = build_case(args.n, args.k, args.nrhs)
     k, nrhs = args.k, args.nrhs
+    node_owned, part, nnode_global = None, None, None
+    if world == 1:
+        m, T, G, F, bfct, bcs = build_case(args.n, args.k, args.nrhs)
+        npatch_total = m.nnode
+    else:
+        # weak scaling: `world` stacked n x n blocks, strip-partitioned by vertex rows
+        from dolfinx_eqlb_b200 import dist as dd, tables as tb
+
+        T = tb.make_tables(k)
+        part, nnode_global = dd.crossed_strip(args.n, rank, world)
+        m, node_owned = part.mesh, part.node_owned
+        G, F = synthetic_inputs(m.ncell, T.ndg, nrhs, seed=SEED + rank)
+        bfct = [m.bfct[m.bfct_side > 0].astype(np.int32) for _ in range(nrhs)]
+        bcs = [[] for _ in range(nrhs)]
+        npatch_total = nnode_global
     if args.path == "se":
-        eq = eqlb.FluxEqlbSE(k, m, F, G)
+        eq = eqlb.FluxEqlbSE(k, m, F, G, node_owned=node_owned)
         nout = m.ncell * T.nrt
     else:
-        eq = eqlb.FluxEqlbEV(k, m, F, G)
+        eq = eqlb.FluxEqlbEV(k, m, F, G, node_owned=node_owned)
         nout = eq.ndofs
     eq.set_boundary_conditions(bfct, bcs)
     prob = eq.problem
@@ -218,6 +233,14 @@ def main():
 
     pG, pF, pS = dptrs(dG), dptrs(dF), dptrs(dS)
 
+    hx = None
+    if world > 1:
+        if args.path == "se":
+            loc, gid = dd.se_dof_gids(part, T.nrt)
+        else:
+            loc, gid = dd.ev_dof_gids(part, k, nnode_global)
+        hx = dd.HaloExchange(loc, gid, device="cuda")
+
     def step_device():
         if args.path == "se":
             rc = lib.eqlb_se_run(prob.h, pG, pF, pS, cabi.c_double_p(), 1)
@@ -225,6 +248,8 @@ def main():
             rc = lib.eqlb_ev_run(prob.h, pG, pF, pS, 1)
         if rc != 0:
             raise RuntimeError(lib.eqlb_last_error().decode())
+        if hx is not None:
+            hx.apply(dS)  # halo sum over NVLink (NCCL send/recv), the only exchange of the path
 
     def barrier():
         if dist is not None:
@@ -251,7 +276,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    npatch_total = m.nnode * world
     value = npatch_total / (ms_step * 1e-3)
 
     # ---- end-to-end through the host API: pinned host buffers, H2D + D2H inside ----
@@ -261,6 +285,14 @@ def main():
     qG, qF, qS = dptrs(hG), dptrs(hF), dptrs(hS)
 
     def step_host():
+        if world > 1:
+            for d, h_ in zip(dG + dF + dS, hG + hF + hS):
+                d.copy_(h_, non_blocking=True)
+            step_device()
+            for d, h_ in zip(dS, hS):
+                h_.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+            return
         if args.path == "se":
             rc = lib.eqlb_se_run(prob.h, qG, qF, qS, cabi.c_double_p(), 0)
         else:
@@ -283,6 +315,9 @@ def main():
     h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF) + sum(s.numel() * 8 for s in hS)
     d2h = sum(s.numel() * 8 for s in hS)
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (the patch kernel is the whole step) ----

@@ -41,6 +41,7 @@ class EqlbMesh(C.Structure):
         ("fct_perms", c_uint8_p),
         ("cell_perm_info", c_uint32_p),
         ("dg_dofmap", c_int32_p),
+        ("node_owned", c_uint8_p),
     ]
 
 
@@ -65,7 +66,7 @@ def _ptr(a, ctype):
 class PackedMesh:
     """Owns contiguous copies of the mesh arrays and the C struct view."""
 
-    def __init__(self, mesh, ndg):
+    def __init__(self, mesh, ndg, node_owned=None):
         from .mesh import dg_dofmap
 
         self.mesh = mesh
@@ -84,6 +85,8 @@ class PackedMesh:
         s.fct_perms = _ptr(keep("fct_perms", mesh.fct_perms, np.uint8), C.c_uint8)
         s.cell_perm_info = _ptr(keep("cell_perm_info", mesh.cell_perm_info, np.uint32), C.c_uint32)
         s.dg_dofmap = _ptr(keep("dg_dofmap", dg_dofmap(mesh.ncell, ndg), np.int32), C.c_int32)
+        if node_owned is not None:
+            s.node_owned = _ptr(keep("node_owned", node_owned, np.uint8), C.c_uint8)
         self.struct = s
 
 

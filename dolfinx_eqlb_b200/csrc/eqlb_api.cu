@@ -54,6 +54,8 @@ void colour_patches(eqlb_handle* h)
   int ncol = 0;
   for (int z = 0; z < n; ++z)
   {
+    if (!h->h_owned[z])
+      continue;
     uint64_t used = 0;
     for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
     {
@@ -74,13 +76,15 @@ void colour_patches(eqlb_handle* h)
   h->ncolours = ncol;
   h->h_colour_off.assign(ncol + 1, 0);
   for (int z = 0; z < n; ++z)
-    h->h_colour_off[h->h_colour[z] + 1]++;
+    if (h->h_owned[z])
+      h->h_colour_off[h->h_colour[z] + 1]++;
   for (int c = 0; c < ncol; ++c)
     h->h_colour_off[c + 1] += h->h_colour_off[c];
   std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
-  h->h_order.resize(n);
+  h->h_order.resize(h->nactive);
   for (int z = 0; z < n; ++z)
-    h->h_order[pos[h->h_colour[z]]++] = z;
+    if (h->h_owned[z])
+      h->h_order[pos[h->h_colour[z]]++] = z;
 }
 
 void append(std::vector<double>& dst, const double* src, size_t n, int& offset)
@@ -120,6 +124,8 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         int ncmax = 0;
         for (int i = 0; i < mesh->nnode; ++i)
         {
+          if (mesh->node_owned && !mesh->node_owned[i])
+            continue;
           const int nc = mesh->node_cell_off[i + 1] - mesh->node_cell_off[i];
           if (nc == 1)
             throw EqlbError(EQLB_ERR_INPUT,
@@ -148,6 +154,12 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->nq = t->nq;
         h->nqf = t->nqf;
         h->ncmax = ncmax;
+        h->h_owned.assign(mesh->nnode, 1);
+        if (mesh->node_owned)
+          h->h_owned.assign(mesh->node_owned, mesh->node_owned + mesh->nnode);
+        h->nactive = 0;
+        for (uint8_t o : h->h_owned)
+          h->nactive += o ? 1 : 0;
 
         const size_t nn = mesh->nnode, nc = mesh->ncell, nf = mesh->nfct;
         h->d_x.upload(mesh->x, nn * 3);
@@ -297,7 +309,9 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
           h->d_node_on_bnd.upload(node_on_stress_bnd, h->nnode);
 
         // patch records (colour-sorted)
-        h->pstride = ((size_t)h->nnode + 31) / 32 * 32;
+        h->pstride = ((size_t)h->nactive + 31) / 32 * 32;
+        if (h->pstride == 0)
+          h->pstride = 32;
         h->d_pnode.alloc(h->pstride);
         h->d_pncells.alloc(h->pstride);
         h->d_pcell.alloc(h->pstride * h->ncmax);

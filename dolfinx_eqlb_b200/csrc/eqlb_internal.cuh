@@ -149,7 +149,9 @@ struct eqlb_handle
   int nnode = 0, ncell = 0, nfct = 0;
   int k = 0, p = 0, nrt = 0, ndg = 0, ndg_fct = 0, ndiv = 0, nadd = 0, nq = 0, nqf = 0;
   int ncmax = 0;
+  int nactive = 0;  // number of equilibrated patches (owned nodes)
   bool dg_identity = true;
+  std::vector<uint8_t> h_owned;
 
   // mesh on device
   DevBuf<double> d_x;

@@ -271,10 +271,11 @@ __global__ void se_dofmap_kernel(MeshView m, const int8_t* __restrict__ facet_ty
                                  int k, int nrt, int nadd, int ndiv, int ndg_fct, int p, bool stress,
                                  const int32_t* __restrict__ closure, const double* __restrict__ cellJ,
                                  int32_t* __restrict__ dofmap, int32_t* __restrict__ projflux,
-                                 int8_t* __restrict__ bmarkers, int ndpc, int hzmax)
+                                 int8_t* __restrict__ bmarkers, int ndpc, int hzmax,
+                                 const uint8_t* __restrict__ owned)
 {
   const int node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= npatch)
+  if (node >= npatch || (owned && !owned[node]))
     return;
   Fan F;
   build_fan(m, facet_type, node, F);
@@ -507,7 +508,7 @@ MeshView eqlb_handle::mesh_view() const
 PatchView eqlb_handle::patch_view() const
 {
   PatchView v;
-  v.npatch = nnode;
+  v.npatch = nactive;
   v.ncmax = ncmax;
   v.nrhs = nrhs;
   v.stride = pstride;
@@ -535,8 +536,10 @@ void launch_patch_builder(eqlb_handle* h, int32_t* x_ncells, int32_t* x_cells, i
   DevBuf<int32_t> d_order;
   d_order.upload(h->h_order.data(), h->h_order.size());
   const int bs = 128;
-  patch_builder_kernel<<<(h->nnode + bs - 1) / bs, bs, 0, h->stream>>>(
-      h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nnode, h->pstride, h->ncmax,
+  if (h->nactive == 0)
+    return;
+  patch_builder_kernel<<<(h->nactive + bs - 1) / bs, bs, 0, h->stream>>>(
+      h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nactive, h->pstride, h->ncmax,
       expand ? nullptr : h->d_pnode.p, h->d_pncells.p, expand ? nullptr : h->d_pcell.p, h->d_pinfo.p,
       expand ? nullptr : h->d_prhs.p, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
   CUDA_CHECK(cudaGetLastError());
@@ -563,10 +566,13 @@ void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, i
     }
   }
   d_closure.upload(closure.data(), closure.size());
+  DevBuf<uint8_t> d_owned;
+  d_owned.upload(h->h_owned.data(), h->h_owned.size());
   const int bs = 128;
   se_dofmap_kernel<<<(h->nnode + bs - 1) / bs, bs, 0, h->stream>>>(
       h->mesh_view(), h->d_facet_type.p, h->nrhs, h->nnode, h->ncmax, h->k, h->nrt, h->nadd, h->ndiv, h->ndg_fct, h->p,
-      (h->flags & EQLB_FLAG_STRESS) != 0, d_closure.p, h->d_cellJ.p, d_dofmap, d_projflux, d_bmarkers, ndpc, hzmax);
+      (h->flags & EQLB_FLAG_STRESS) != 0, d_closure.p, h->d_cellJ.p, d_dofmap, d_projflux, d_bmarkers, ndpc, hzmax,
+      d_owned.p);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->launches++;

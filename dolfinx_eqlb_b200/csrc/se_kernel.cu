@@ -801,7 +801,9 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   const size_t bstride = (size_t)h->ncell * h->nrt;
   if (atomics)
   {
-    const int count = h->nnode;
+    const int count = h->nactive;
+    if (count == 0)
+      return;
     kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, 0, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
                                                         h->d_bflux.p, bstride, 1, h->d_cell_fct.p, h->nfct);
     CUDA_CHECK(cudaGetLastError());

@@ -66,6 +66,8 @@ typedef struct eqlb_mesh {
   const uint8_t*  fct_perms;      /* [ncell*3]  topology().get_facet_permutations()  */
   const uint32_t* cell_perm_info; /* [ncell]    topology().get_cell_permutation_info() */
   const int32_t*  dg_dofmap;      /* [ncell*ndg] dofmap of the DG_p space of G and f */
+  const uint8_t*  node_owned;     /* [nnode] 1 = equilibrate the patch of this node (index_map(0) owned
+                                     nodes, `se/reconstruction.hpp:90`); NULL = all nodes          */
 } eqlb_mesh;
 
 /* Reference-element tables (dolfinx_eqlb_b200/tables.py; Basix-derived in a

@@ -594,6 +594,8 @@ int oracle_ev_run(const eqlb_mesh* mesh, const eqlb_tables* tables, int nrhs, co
 
     for (int node = 0; node < mesh->nnode; ++node)
     {
+      if (mesh->node_owned && !mesh->node_owned[node])
+        continue;
       patch.create_subdofmap(node);
       const int ncells = patch.ncells;
       const int ndof_patch = patch.ndof_patch_nz, n = ndof_patch + 1;

@@ -96,7 +96,8 @@ struct Patch
     for (int i = 0; i < nnodes; ++i)
     {
       int nc = mv.node_to_cell(i).size();
-      if (nc == ncells_min)
+      const bool owned = !(mv.m->node_owned && !mv.m->node_owned[i]);
+      if (owned && nc == ncells_min)
         throw std::runtime_error("Patch around node " + std::to_string(i) + " has only "
                                  + std::to_string(ncells_min) + " cells.");
       ncells_max = std::max(ncells_max, nc);

@@ -89,9 +89,9 @@ class BCData:
         self.node_on_stress_bnd = None if node_on_stress_bnd is None else np.ascontiguousarray(node_on_stress_bnd, dtype=np.int8)
 
 
-def se_run(mesh, tables, bc: BCData, G, F, stress=False, korn=False, sigma0=None):
+def se_run(mesh, tables, bc: BCData, G, F, stress=False, korn=False, sigma0=None, node_owned=None):
     """oracle of `reconstruct_fluxes_semiexplt` -> list of DRT vectors [ncell*nrt]."""
-    pm, pt = PackedMesh(mesh, tables.ndg), PackedTables(tables)
+    pm, pt = PackedMesh(mesh, tables.ndg, node_owned), PackedTables(tables)
     nrhs = bc.nrhs
     G = [np.ascontiguousarray(g, dtype=np.float64) for g in G]
     F = [np.ascontiguousarray(f, dtype=np.float64) for f in F]
@@ -150,9 +150,9 @@ def ev_ndofs(mesh, tables):
     return mesh.nfct * k + mesh.ncell * (k * k - k)
 
 
-def ev_run(mesh, tables, bc: BCData, G, F, sigma0=None):
+def ev_run(mesh, tables, bc: BCData, G, F, sigma0=None, node_owned=None):
     """oracle of `reconstruct_fluxes_minimisation` -> conforming hierarchic-RT vectors."""
-    pm, pt = PackedMesh(mesh, tables.ndg), PackedTables(tables)
+    pm, pt = PackedMesh(mesh, tables.ndg, node_owned), PackedTables(tables)
     nrhs = bc.nrhs
     G = [np.ascontiguousarray(g, dtype=np.float64) for g in G]
     F = [np.ascontiguousarray(f, dtype=np.float64) for f in F]

@@ -1,0 +1,76 @@
+"""2-GPU NCCL test: strip-partitioned equilibration + halo sum equals the single-GPU
+result (skipped on boxes with fewer than 2 GPUs)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, path, k, out):
+    import torch.distributed as dist
+
+    from common import make_mesh
+    from dolfinx_eqlb_b200 import dist as dd, eqlb, tables as tb
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    m = make_mesh("crossed", 12, 3, perturb=0.2)
+    T = tb.make_tables(k)
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal(m.ncell * T.ndg * 2)
+    F = rng.standard_normal(m.ncell * T.ndg)
+    part = dd.extract_local(m, dd.strip_owner(m, world), rank)
+    lm = part.mesh
+    Gl = G.reshape(m.ncell, -1)[part.cell_gid].ravel()
+    Fl = F.reshape(m.ncell, -1)[part.cell_gid].ravel()
+    cls = eqlb.FluxEqlbSE if path == "se" else eqlb.FluxEqlbEV
+    eq = cls(k, lm, [Fl], [Gl], node_owned=part.node_owned)
+    eq.set_boundary_conditions([lm.bfct[lm.bfct_side > 0].astype(np.int32)], [[]])
+    eq.equilibrate_fluxes()
+    loc, gid = dd.se_dof_gids(part, T.nrt) if path == "se" else dd.ev_dof_gids(part, k, m.nnode)
+    x = torch.from_numpy(eq.list_flux[0]).cuda()
+    dd.HaloExchange(loc, gid, device="cuda").apply([x])
+    # single-GPU reference of the whole mesh on this rank's device
+    ref_eq = cls(k, m, [F], [G])
+    ref_eq.set_boundary_conditions([m.boundary_facets([1, 2, 3, 4])], [[]])
+    ref_eq.equilibrate_fluxes()
+    ref = ref_eq.list_flux[0]
+    if path == "se":
+        ref_l = ref.reshape(m.ncell, T.nrt)[part.cell_gid].ravel()
+    else:
+        key_g = m.fct_node[:, 0].astype(np.int64) * m.nnode + m.fct_node[:, 1]
+        fl = np.searchsorted(key_g, part.fct_gid(m.nnode))
+        ncd = k * k - k
+        ref_l = np.concatenate([ref[: m.nfct * k].reshape(m.nfct, k)[fl].ravel(), ref[m.nfct * k :].reshape(m.ncell, ncd)[part.cell_gid].ravel()])
+    out[rank] = float(np.abs(x.cpu().numpy() - ref_l).max() / np.abs(ref_l).max())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("path,k", [("se", 2), ("ev", 2), ("se", 3)])
+def test_two_gpu_halo_sum(path, k):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(2, port, path, k, out), nprocs=2, join=True)
+        res = dict(out)
+    assert len(res) == 2
+    for e in res.values():
+        assert e < 1e-12

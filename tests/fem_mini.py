@@ -247,3 +247,82 @@ def conforming_to_drt(mesh, T, sig_g):
     if ncd:
         out[:, 3 * k :] = sig_g[mesh.nfct * k :].reshape(mesh.ncell, ncd)
     return out.reshape(-1)
+
+
+def solve_elasticity(mesh, q, T, f_dg, dirichlet_sides, neumann=None, mu=1.0, lam=1.5):
+    """-div sigma(u) = f, sigma = 2 mu eps(u) + lam tr(eps) I, u = 0 on the Dirichlet sides,
+    (-sigma) n = g on the Neumann facets (rows of the 'flux' -sigma).  f_dg: two DG_p
+    vectors; neumann: two dicts facet -> coefficients (one per row).  Returns the two
+    projected flux rows G_r = -sigma_r(u_h) as DG_p coefficient vectors."""
+    V = LagrangeSpace(mesh, q)
+    J, K, det = jacobians(mesh)
+    qp, qw = tb.cell_quadrature(2 * max(q, T.p + 1))
+    phi, dphi = tabulate_scalar(V.basis, qp)
+    dgv, _ = tabulate_scalar(T.extra["dg_exact"], qp)
+    g = np.einsum("cji,qnj->cqni", K, dphi)  # [c][q][n][2] physical gradients
+    nl = V.nloc
+    wdet = np.einsum("q,c->cq", qw, np.abs(det))
+    # B-matrix free assembly: eps(u):eps(v) and div div
+    Ke = np.zeros((mesh.ncell, 2 * nl, 2 * nl))
+    for a in range(2):
+        for b in range(2):
+            # u component a, v component b
+            blk = lam * np.einsum("cq,cqn,cqm->cnm", wdet, g[..., b], g[..., a])  # div v * div u
+            blk += mu * np.einsum("cq,cqn,cqm->cnm", wdet, g[..., a], g[..., b])  # grad_a v_b * grad_b u_a
+            if a == b:
+                blk += mu * np.einsum("cq,cqni,cqmi->cnm", wdet, g, g)
+            Ke[:, b::2, a::2] = blk
+    dm2 = np.stack([2 * V.dofmap, 2 * V.dofmap + 1], axis=2).reshape(mesh.ncell, 2 * nl)
+    rows = np.repeat(dm2, 2 * nl, axis=1).ravel()
+    cols = np.tile(dm2, (1, 2 * nl)).ravel()
+    A = sp.csr_matrix((Ke.ravel(), (rows, cols)), shape=(2 * V.ndof, 2 * V.ndof))
+    b = np.zeros(2 * V.ndof)
+    for r in range(2):
+        fq = np.einsum("qi,ci->cq", dgv, f_dg[r].reshape(mesh.ncell, T.ndg))
+        be = np.einsum("cq,cq,qn->cn", wdet, fq, phi)
+        np.add.at(b, (2 * V.dofmap + r).ravel(), be.ravel())
+        if neumann and neumann[r]:
+            gs, gwt = tb.gauss_legendre_01(q + T.k + 1)
+            for fct, gc in neumann[r].items():
+                c = mesh.fct_cell[mesh.fct_cell_off[fct]]
+                lf = int(np.nonzero(mesh.cell_fct[c] == fct)[0][0])
+                a_, b_ = FACET_VERTS[lf]
+                pts = [tb.facet_point(lf, s) for s in gs]
+                pv, _ = tabulate_scalar(V.basis, pts)
+                length = np.linalg.norm(mesh.x[mesh.cell_node[c, a_], :2] - mesh.x[mesh.cell_node[c, b_], :2])
+                gval = sum(gc[j] * gs**j for j in range(len(gc)))
+                b[2 * V.dofmap[c] + r] -= length * (gwt * gval) @ pv
+    bd = V.boundary_dofs(dirichlet_sides)
+    bd2 = np.concatenate([2 * bd, 2 * bd + 1])
+    free = np.setdiff1d(np.arange(2 * V.ndof), bd2)
+    u = np.zeros(2 * V.ndof)
+    u[free] = spla.spsolve(A[free][:, free].tocsc(), b[free])
+    nodes = [(float(a), float(b_)) for a, b_ in tb.lagrange_nodes(T.p)]
+    _, dn = tabulate_scalar(V.basis, nodes)
+    gn = np.einsum("cji,qnj->cqni", K, dn)  # [c][node][n][2]
+    ux = np.einsum("cqni,cn->cqi", gn, u[2 * V.dofmap])  # grad u_x
+    uy = np.einsum("cqni,cn->cqi", gn, u[2 * V.dofmap + 1])
+    tr = ux[..., 0] + uy[..., 1]
+    s00 = 2 * mu * ux[..., 0] + lam * tr
+    s11 = 2 * mu * uy[..., 1] + lam * tr
+    s01 = mu * (ux[..., 1] + uy[..., 0])
+    G0 = -np.stack([s00, s01], axis=2).reshape(-1)
+    G1 = -np.stack([s01, s11], axis=2).reshape(-1)
+    return [G0, G1]
+
+
+def check_weak_symmetry(mesh, T, sig0, sig1):
+    """max_z |int (sigma_01 - sigma_10) hat_z| relative (check_eqlb_conditions.py:476-521)."""
+    J, K, det = jacobians(mesh)
+    rv, _ = tabulate_rt(T, T.qpts)
+    hat = T.hat_q
+    c0 = sig0.reshape(mesh.ncell, T.nrt)
+    c1 = sig1.reshape(mesh.ncell, T.nrt)
+    s0 = np.einsum("cij,qnj,cn->cqi", J, rv, c0) / det[:, None, None]
+    s1 = np.einsum("cij,qnj,cn->cqi", J, rv, c1) / det[:, None, None]
+    asym = s0[..., 1] - s1[..., 0]
+    loc = np.einsum("q,c,cq,qv->cv", T.qwts, np.abs(det), asym, hat)
+    tot = np.zeros(mesh.nnode)
+    np.add.at(tot, mesh.cell_node.ravel(), loc.ravel())
+    scale = np.einsum("q,c,cq->c", T.qwts, np.abs(det), np.abs(s0[..., 1]) + np.abs(s1[..., 0])).max()
+    return np.abs(tot).max() / max(scale, 1e-300)

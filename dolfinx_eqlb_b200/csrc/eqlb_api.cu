@@ -52,9 +52,10 @@ void colour_patches(eqlb_handle* h)
   const int n = h->nnode;
   h->h_colour.assign(n, -1);
   int ncol = 0;
+  const int ngrouped = h->h_group_off.empty() ? 0 : h->h_group_off.back();
   for (int z = 0; z < n; ++z)
   {
-    if (!h->h_owned[z])
+    if (!h->h_owned[z] || h->h_grouped[z])
       continue;
     uint64_t used = 0;
     for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
@@ -76,14 +77,15 @@ void colour_patches(eqlb_handle* h)
   h->ncolours = ncol;
   h->h_colour_off.assign(ncol + 1, 0);
   for (int z = 0; z < n; ++z)
-    if (h->h_owned[z])
+    if (h->h_owned[z] && !h->h_grouped[z])
       h->h_colour_off[h->h_colour[z] + 1]++;
+  h->h_colour_off[0] = ngrouped;  // grouped patches occupy the head of h_order
   for (int c = 0; c < ncol; ++c)
     h->h_colour_off[c + 1] += h->h_colour_off[c];
   std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
   h->h_order.resize(h->nactive);
   for (int z = 0; z < n; ++z)
-    if (h->h_owned[z])
+    if (h->h_owned[z] && !h->h_grouped[z])
       h->h_order[pos[h->h_colour[z]]++] = z;
 }
 
@@ -176,6 +178,10 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
         h->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
         h->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
+        h->h_node_fct_off.assign(mesh->node_fct_off, mesh->node_fct_off + nn + 1);
+        h->h_node_fct.assign(mesh->node_fct, mesh->node_fct + mesh->node_fct_off[nn]);
+        h->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
+        h->h_grouped.assign(nn, 0);
 
         // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
         h->dg_identity = true;
@@ -306,7 +312,68 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
           if (bflux && bflux[r])
             CUDA_CHECK(cudaMemcpy(h->d_bflux.p + (size_t)r * nb, bflux[r], nb * sizeof(double), cudaMemcpyHostToDevice));
         if (node_on_stress_bnd)
+        {
           h->d_node_on_bnd.upload(node_on_stress_bnd, h->nnode);
+          // grouped boundary patches (se/reconstruction.hpp:170-234, k == 2 only): 2-cell
+          // patches on a pure traction boundary are solved together with the adjacent
+          // patch, which then imposes weak symmetry on the accumulated global stress
+          h->h_grouped.assign(h->nnode, 0);
+          h->h_group_off.clear();
+          std::vector<int32_t> gorder;
+          if ((h->flags & EQLB_FLAG_STRESS) && h->k == 2)
+          {
+            auto ncells_of = [&](int z) { return h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]; };
+            std::vector<uint8_t> perform(h->nnode, 1);
+            for (int z = 0; z < h->nnode; ++z)
+            {
+              if (!(node_on_stress_bnd[z] && perform[z] && h->h_owned[z]) || ncells_of(z) != 2)
+                continue;
+              // adjacent_internal_patch (se/Patch.cpp:761-784)
+              int inner = -1;
+              for (int i = h->h_node_fct_off[z]; i < h->h_node_fct_off[z + 1]; ++i)
+              {
+                const int32_t fct = h->h_node_fct[i];
+                if (facet_type[fct] == EQLB_FCT_INTERNAL)
+                {
+                  inner = (h->h_fct_node[2 * fct] == z) ? h->h_fct_node[2 * fct + 1] : h->h_fct_node[2 * fct];
+                  break;
+                }
+              }
+              // group_boundary_patches (se/Patch.cpp:60-104)
+              std::vector<int32_t> grouped{inner};
+              for (int i = h->h_node_cell_off[inner]; i < h->h_node_cell_off[inner + 1]; ++i)
+                for (int j = 0; j < 3; ++j)
+                {
+                  const int32_t pnt = h->h_cell_node[3 * (size_t)h->h_node_cell[i] + j];
+                  if (node_on_stress_bnd[pnt] && std::find(grouped.begin(), grouped.end(), pnt) == grouped.end()
+                      && ncells_of(pnt) == 2)
+                    grouped.push_back(pnt);
+                }
+              if (grouped.size() < 2)
+                continue;
+              if (h->h_group_off.empty())
+                h->h_group_off.push_back(0);
+              for (int32_t q : grouped)
+              {
+                if (!perform[q] || !h->h_owned[q])
+                  throw EqlbError(EQLB_ERR_INPUT,
+                                  "Incompatible mesh! To many patches with 2 cells on neumann boundary.");
+                perform[q] = 0;
+                h->h_grouped[q] = 1;
+                gorder.push_back(q);
+              }
+              h->h_group_off.push_back((int32_t)gorder.size());
+            }
+          }
+          colour_patches(h);
+          std::copy(gorder.begin(), gorder.end(), h->h_order.begin());
+        }
+        else
+        {
+          h->h_grouped.assign(h->nnode, 0);
+          h->h_group_off.clear();
+          colour_patches(h);
+        }
 
         // patch records (colour-sorted)
         h->pstride = ((size_t)h->nactive + 31) / 32 * 32;

@@ -161,7 +161,9 @@ struct eqlb_handle
   DevBuf<double> d_cellJ;  // [ncell][4] Jacobians (J00,J01,J10,J11)
 
   // host copies needed for colouring / validation
-  std::vector<int32_t> h_node_cell_off, h_node_cell, h_cell_node;
+  std::vector<int32_t> h_node_cell_off, h_node_cell, h_cell_node, h_node_fct_off, h_node_fct, h_fct_node;
+  std::vector<uint8_t> h_grouped;      // node is member of a grouped boundary patch set
+  std::vector<int32_t> h_group_off;    // offsets of the groups in h_order (first member = inner patch)
 
   // tables
   DevBuf<double> d_tables;
@@ -200,3 +202,4 @@ void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, i
 void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn);
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma);
 void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* const* dout);
+void launch_korn(eqlb_handle* h, double* dKorn);

@@ -44,11 +44,11 @@ __device__ __forceinline__ int tri(int i, int j) { return i >= j ? i * (i + 1) /
 //             (+ the mean-value shift the reference's Lagrange multiplier produces),
 //             then || sigma_p + Z u - hat G || -> min over the same patch-wise H(div=0)
 //             basis Z; output into the conforming hierarchic RT vector.
-template <int K, int NDG, int NCMAX, bool EV>
+template <int K, int NDG, int NCMAX, bool EV, bool STRESS>
 __global__ void __launch_bounds__(128)
 patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __restrict__ cellJ,
              const int32_t* __restrict__ dgmap, int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux,
-             size_t bflux_stride, int use_atomics, const int32_t* __restrict__ cell_fct, int nfct)
+             size_t bflux_stride, int use_atomics, const int32_t* __restrict__ cell_fct, int nfct, int mode)
 {
   using D = SeDims<K>;
   constexpr int k = K, ndiv = D::ndiv, nadd = D::nadd, nrt = D::nrt, nact = D::nact, ncol = D::ncol, nz = D::nz;
@@ -111,6 +111,8 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
   double mm[NCMAX][K], mp[NCMAX][K];  // own-side facet moments on E_{a-1} / E_a
   double cm[NCMAX][NT];               // cell moments
   double cf[NCMAX][ncol];             // sigma-tilde coefficients: [E_{a-1} (k)][E_a (k)][add][div]
+  double cfin[STRESS ? 2 : 1][NCMAX][ncol];  // final patch coefficients of the two stress rows
+  const double* __restrict__ t_p1 = s_tab + tv.o_rt_p1;  // [nrt][2][3]
   double A[HZ * (HZ + 1) / 2];
   double L[HZ];
 
@@ -125,7 +127,12 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
     const bool internal = (ptype == EQLB_PATCH_INTERNAL);
     const int nf = internal ? nc : nc + 1;
     const int hz = 1 + (k - 1) * nf + nadd * nc;
-
+    const int offset_En = nc * (k - 1);
+    // mode 1 (grouped patches, se/reconstruction.hpp:170-234): no equilibration of this
+    // patch, the stress coefficients come from the accumulated global vectors
+    // (impose_weak_symmetry<modified_patch = true>, se/solve_patch_weaksym.hpp:100-131)
+    if (mode == 0)
+    {
     // ---- moments of every cell ----
 #pragma unroll 1
     for (int a = 0; a < nc; ++a)
@@ -409,7 +416,6 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
 
     // ---- step 2: assemble the patch system ----
     const bool req_bc = (ptype == EQLB_PATCH_ESSNT_DUAL || ptype == EQLB_PATCH_MIXED);
-    const int offset_En = nc * (k - 1);
     auto marked = [&](int pd) -> bool
     {
       if (!req_bc)
@@ -744,6 +750,21 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
         }
         continue;
       }
+      if (STRESS && r < 2)
+      {
+#pragma unroll
+        for (int j = 0; j < k; ++j)
+        {
+          cfin[r][a][j] = cf[a][j] + um[j];
+          cfin[r][a][k + j] = cf[a][k + j] + up[j];
+        }
+#pragma unroll
+        for (int i = 0; i < nadd; ++i)
+          cfin[r][a][2 * k + i] = cf[a][2 * k + i] + L[nf * (k - 1) + 1 + a * nadd + i];
+#pragma unroll
+        for (int t = 0; t < ndiv; ++t)
+          cfin[r][a][2 * k + nadd + t] = cf[a][2 * k + nadd + t];
+      }
       double* dst = sig + (size_t)cell[a] * nrt;
       if (use_atomics)
       {
@@ -776,6 +797,461 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
           dst[3 * k + t] += cf[a][2 * k + nadd + t];
       }
     }
+    }  // mode == 0
+
+    // ---- weak symmetry of the stress rows 0/1 (se/solve_patch_weaksym.hpp:59-233) ----
+    if constexpr (STRESS && !EV)
+    {
+      if (r == 1)
+      {
+        constexpr int NCS = NCMAX + 3;  // P1 constraint dofs (n_f + 1 <= NCMAX + 2) + mean-value multiplier
+        const int ncs = nf + 1;
+        int rtype[2];
+        bool rrev[2];
+        bool need_bc = false, lagr = true;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+        {
+          const uint8_t q = pv.rhsinfo[(size_t)rr * pv.stride + ip];
+          rtype[rr] = q & 3;
+          rrev[rr] = (q & 4) != 0;
+          if (rtype[rr] == EQLB_PATCH_ESSNT_DUAL || rtype[rr] == EQLB_PATCH_MIXED)
+            need_bc = true;
+          if (rtype[rr] == EQLB_PATCH_ESSNT_PRIMAL || rtype[rr] == EQLB_PATCH_MIXED)
+            lagr = false;  // se/PatchData.hpp:189-205
+        }
+        auto marked_row = [&](int rr, int pd) -> bool
+        {
+          const int tp = rtype[rr];
+          if (!(tp == EQLB_PATCH_ESSNT_DUAL || tp == EQLB_PATCH_MIXED))
+            return false;
+          if (pd == 0)
+            return true;
+          if (pd >= 1 + (k - 1) * nf)
+            return false;
+          const bool onE0 = pd < k;
+          const bool onEn = pd > offset_En && pd < offset_En + k;
+          if (tp == EQLB_PATCH_ESSNT_DUAL)
+            return onE0 || onEn;
+          return rrev[rr] ? onEn : onE0;
+        };
+        double Bm[2][HZ][NCS - 1];
+        double Cm[NCS][NCS];
+        double Lc[NCS];
+        double Fk[2][HZ * (HZ + 1) / 2];
+        for (int i = 0; i < hz; ++i)
+          for (int c2 = 0; c2 < ncs; ++c2)
+          {
+            Bm[0][i][c2] = 0.0;
+            Bm[1][i][c2] = 0.0;
+          }
+        for (int i = 0; i <= ncs; ++i)
+        {
+          Lc[i] = 0.0;
+          for (int c2 = 0; c2 <= ncs; ++c2)
+            Cm[i][c2] = 0.0;
+        }
+        for (int i = 0; i < hz * (hz + 1) / 2; ++i)
+          A[i] = 0.0;
+
+#pragma unroll 1
+        for (int a = 0; a < nc; ++a)
+        {
+          const int v = info[a] & 3, fm = (info[a] >> 2) & 3, fp = (info[a] >> 4) & 3;
+          const bool rev0 = (info[a] & 64) != 0;
+          if (mode == 1)
+          {
+            // accumulated global stress on the cell; the dofs of the third facet (which
+            // other patches of the group have filled) enter L_c below
+            const double sgn3 = detJ[a] > 0.0 ? 1.0 : -1.0;
+            const double* ad3 = adj[a];
+            const int f3 = 3 - fm - fp;
+            const int vl3[3] = {v, 3 - fp - v, 3 - fm - v};
+            const int cd3[3] = {0, (!internal && a == nc - 1) ? nf : a + 1, (a == 0) ? (internal ? nc : nf - 1) : a};
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+            {
+              const double* src = ptrs.S[rr] + (size_t)cell[a] * nrt;
+#pragma unroll
+              for (int j = 0; j < k; ++j)
+              {
+                cfin[rr][a][j] = src[fm * k + j];
+                cfin[rr][a][k + j] = src[fp * k + j];
+              }
+#pragma unroll
+              for (int i = 0; i < nadd; ++i)
+                cfin[rr][a][2 * k + i] = src[3 * k + ndiv + i];
+#pragma unroll
+              for (int t = 0; t < ndiv; ++t)
+                cfin[rr][a][2 * k + nadd + t] = src[3 * k + t];
+#pragma unroll
+              for (int j = 0; j < k; ++j)
+              {
+                const double c3 = src[f3 * k + j];
+                const double* tp = t_p1 + (f3 * k + j) * 6;
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj)
+                {
+                  const double px = sgn3 * (ad3[3] * tp[vl3[jj]] - ad3[1] * tp[3 + vl3[jj]]);
+                  const double py = sgn3 * (-ad3[2] * tp[vl3[jj]] + ad3[0] * tp[3 + vl3[jj]]);
+                  Lc[cd3[jj]] -= (rr == 0) ? c3 * py : -c3 * px;
+                }
+              }
+            }
+          }
+          auto rdof = [&](int q) -> int
+          {
+            if (q < k)
+              return fm * k + q;
+            if (q < 2 * k)
+              return fp * k + (q - k);
+            if (q < 2 * k + nadd)
+              return 3 * k + ndiv + (q - 2 * k);
+            return 3 * k + (q - 2 * k - nadd);
+          };
+          // constraint slots: patch node, outer node of E_a, outer node of E_{a-1}
+          const int vl[3] = {v, 3 - fp - v, 3 - fm - v};
+          const int cd[3] = {0, (!internal && a == nc - 1) ? nf : a + 1, (a == 0) ? (internal ? nc : nf - 1) : a};
+          const double sgn = detJ[a] > 0.0 ? 1.0 : -1.0;
+          const double* ad = adj[a];
+          const double J00 = sgn * ad[3], J01 = -sgn * ad[1], J10 = -sgn * ad[2], J11 = sgn * ad[0];
+          // P[q][d][j] = int_T phi_q^d lambda_j  (physical)
+          double P[ncol][2][3];
+#pragma unroll
+          for (int q = 0; q < ncol; ++q)
+          {
+            const double* tp = t_p1 + rdof(q) * 6;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+              P[q][0][j] = J00 * tp[vl[j]] + J01 * tp[3 + vl[j]];
+              P[q][1][j] = J10 * tp[vl[j]] + J11 * tp[3 + vl[j]];
+            }
+          }
+          // L_c = -(sigma_01 - sigma_10, psi), mean-value row
+          const double ce = fabs(detJ[a]) * (1.0 / 6.0);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+          {
+            double sj = 0.0;
+#pragma unroll
+            for (int q = 0; q < ncol; ++q)
+              sj += cfin[0][a][q] * P[q][1][j] - cfin[1][a][q] * P[q][0][j];
+            Lc[cd[j]] -= sj;
+            if (lagr)
+            {
+              Cm[cd[j]][ncs] += ce;
+              Cm[ncs][cd[j]] += ce;
+            }
+          }
+          // mass block of the H(div=0) functions (no BC masks: A_rec)
+          double MB[nact][nact];
+          const double g0 = gm[a][0], g1 = gm[a][1], g2 = gm[a][2];
+#pragma unroll
+          for (int q = 0; q < nact; ++q)
+#pragma unroll
+            for (int s2 = 0; s2 < nact; ++s2)
+            {
+              const int o = rdof(q) * nrt + rdof(s2);
+              MB[q][s2] = g0 * t_mass[o] + g1 * t_mass[nrt * nrt + o] + g2 * t_mass[2 * nrt * nrt + o];
+            }
+          if (rev0)
+          {
+            double tmp[K];
+#pragma unroll
+            for (int s2 = 0; s2 < nact; ++s2)
+            {
+#pragma unroll
+              for (int i = 0; i < k; ++i)
+              {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < k; ++j)
+                  acc += t_trafo[i * k + j] * MB[j][s2];
+                tmp[i] = acc;
+              }
+#pragma unroll
+              for (int i = 0; i < k; ++i)
+                MB[i][s2] = tmp[i];
+            }
+#pragma unroll
+            for (int q = 0; q < nact; ++q)
+            {
+#pragma unroll
+              for (int i = 0; i < k; ++i)
+              {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < k; ++j)
+                  acc += t_trafo[i * k + j] * MB[q][j];
+                tmp[i] = acc;
+              }
+#pragma unroll
+              for (int i = 0; i < k; ++i)
+                MB[q][i] = tmp[i];
+            }
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+              {
+#pragma unroll
+                for (int i = 0; i < k; ++i)
+                {
+                  double acc = 0.0;
+#pragma unroll
+                  for (int q = 0; q < k; ++q)
+                    acc += t_trafo[i * k + q] * P[q][d][j];
+                  tmp[i] = acc;
+                }
+#pragma unroll
+                for (int i = 0; i < k; ++i)
+                  P[i][d][j] = tmp[i];
+              }
+          }
+          const int am = (a == 0) ? nc - 1 : a - 1;
+          const double p_ea = -pp[a];
+          const double p_em = rev0 ? -pp[am] : pm[a];
+          auto sgn_of = [&](int q) -> double { return q < k ? p_em : (q < 2 * k ? p_ea : 1.0); };
+          auto pdof = [&](int i) -> int
+          {
+            if (i < k - 1)
+              return a * (k - 1) + i + 1;
+            if (i == k - 1)
+              return 0;
+            if (i < 2 * k - 1)
+              return ((internal && a == nc - 1) ? 0 : (a + 1) * (k - 1)) + (i - k + 1);
+            return nf * (k - 1) + 1 + a * nadd + (i - (2 * k - 1));
+          };
+#pragma unroll
+          for (int i = 0; i < nz; ++i)
+          {
+            const int qi = i + 1;
+            const int di = pdof(i);
+            // B_1 = (psi_y, lambda), B_2 = -(psi_x, lambda)   (se/stressmin_kernel.hpp:214-222)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+              double py, px;
+              if (i == k - 1)
+              {
+                py = p_em * P[0][1][j] + p_ea * P[k][1][j];
+                px = p_em * P[0][0][j] + p_ea * P[k][0][j];
+              }
+              else
+              {
+                py = sgn_of(qi) * P[qi][1][j];
+                px = sgn_of(qi) * P[qi][0][j];
+              }
+              Bm[0][di][cd[j]] += py;
+              Bm[1][di][cd[j]] -= px;
+            }
+#pragma unroll
+            for (int j = 0; j < nz; ++j)
+            {
+              const int dj = pdof(j);
+              if (dj > di)
+                continue;
+              const int qj = j + 1;
+              double val;
+              if (i == k - 1 && j == k - 1)
+                val = MB[0][0] + MB[k][k] + 2.0 * p_em * p_ea * MB[0][k];
+              else if (i == k - 1)
+                val = sgn_of(qj) * (p_em * MB[0][qj] + p_ea * MB[k][qj]);
+              else if (j == k - 1)
+                val = sgn_of(qi) * (p_em * MB[qi][0] + p_ea * MB[qi][k]);
+              else
+                val = sgn_of(qi) * sgn_of(qj) * MB[qi][qj];
+              A[tri(di, dj)] += val;
+            }
+          }
+        }
+
+        // Schur complement C -= B_k^T A_k^-1 B_k  (se/PatchData.hpp:604-628)
+        double xcol[HZ];
+        for (int kk = 0; kk < 2; ++kk)
+        {
+          double* F = Fk[(need_bc && kk == 1) ? 1 : 0];
+          if (kk == 0 || need_bc)
+          {
+            for (int i = 0; i < hz; ++i)
+              for (int j = 0; j <= i; ++j)
+              {
+                const bool mi = marked_row(kk, i), mj = marked_row(kk, j);
+                F[tri(i, j)] = (mi || mj) ? ((i == j) ? 1.0 : 0.0) : A[tri(i, j)];
+              }
+            for (int j = 0; j < hz; ++j)
+            {
+              double d = F[tri(j, j)];
+              for (int q = 0; q < j; ++q)
+                d -= F[tri(j, q)] * F[tri(j, q)];
+              d = sqrt(d);
+              F[tri(j, j)] = d;
+              const double id = 1.0 / d;
+              for (int i = j + 1; i < hz; ++i)
+              {
+                double s2 = F[tri(i, j)];
+                for (int q = 0; q < j; ++q)
+                  s2 -= F[tri(i, q)] * F[tri(j, q)];
+                F[tri(i, j)] = s2 * id;
+              }
+            }
+          }
+          for (int c2 = 0; c2 < ncs; ++c2)
+          {
+            for (int i = 0; i < hz; ++i)
+              xcol[i] = marked_row(kk, i) ? 0.0 : Bm[kk][i][c2];
+            for (int i = 0; i < hz; ++i)
+            {
+              double s2 = xcol[i];
+              for (int q = 0; q < i; ++q)
+                s2 -= F[tri(i, q)] * xcol[q];
+              xcol[i] = s2 / F[tri(i, i)];
+            }
+            for (int i = hz - 1; i >= 0; --i)
+            {
+              double s2 = xcol[i];
+              for (int q = i + 1; q < hz; ++q)
+                s2 -= F[tri(q, i)] * xcol[q];
+              xcol[i] = s2 / F[tri(i, i)];
+            }
+            for (int rr = 0; rr < ncs; ++rr)
+            {
+              double s2 = 0.0;
+              for (int i = 0; i < hz; ++i)
+                s2 += (marked_row(kk, i) ? 0.0 : Bm[kk][i][rr]) * xcol[i];
+              Cm[rr][c2] -= s2;
+            }
+          }
+        }
+        // partial-pivot LU of the Schur complement (se/PatchData.hpp:630-637)
+        const int dim_c = lagr ? ncs + 1 : ncs;
+        for (int p2 = 0; p2 < dim_c; ++p2)
+        {
+          int piv = p2;
+          double mx = fabs(Cm[p2][p2]);
+          for (int i = p2 + 1; i < dim_c; ++i)
+            if (fabs(Cm[i][p2]) > mx)
+            {
+              mx = fabs(Cm[i][p2]);
+              piv = i;
+            }
+          if (piv != p2)
+          {
+            for (int j = 0; j < dim_c; ++j)
+            {
+              const double tmpv = Cm[p2][j];
+              Cm[p2][j] = Cm[piv][j];
+              Cm[piv][j] = tmpv;
+            }
+            const double tl = Lc[p2];
+            Lc[p2] = Lc[piv];
+            Lc[piv] = tl;
+          }
+          const double dinv = 1.0 / Cm[p2][p2];
+          for (int i = p2 + 1; i < dim_c; ++i)
+          {
+            const double l = Cm[i][p2] * dinv;
+            for (int j = p2 + 1; j < dim_c; ++j)
+              Cm[i][j] -= l * Cm[p2][j];
+            Lc[i] -= l * Lc[p2];
+          }
+        }
+        for (int i = dim_c - 1; i >= 0; --i)
+        {
+          double s2 = Lc[i];
+          for (int j = i + 1; j < dim_c; ++j)
+            s2 -= Cm[i][j] * Lc[j];
+          Lc[i] = s2 / Cm[i][i];
+        }
+        // u_k = A_k^-1 (-B_k u_c) and scatter into both rows (:170-232)
+        for (int kk = 0; kk < 2; ++kk)
+        {
+          const double* F = Fk[(need_bc && kk == 1) ? 1 : 0];
+          for (int i = 0; i < hz; ++i)
+          {
+            double s2 = 0.0;
+            if (!marked_row(kk, i))
+              for (int c2 = 0; c2 < ncs; ++c2)
+                s2 -= Bm[kk][i][c2] * Lc[c2];
+            xcol[i] = s2;
+          }
+          for (int i = 0; i < hz; ++i)
+          {
+            double s2 = xcol[i];
+            for (int q = 0; q < i; ++q)
+              s2 -= F[tri(i, q)] * xcol[q];
+            xcol[i] = s2 / F[tri(i, i)];
+          }
+          for (int i = hz - 1; i >= 0; --i)
+          {
+            double s2 = xcol[i];
+            for (int q = i + 1; q < hz; ++q)
+              s2 -= F[tri(q, i)] * xcol[q];
+            xcol[i] = s2 / F[tri(i, i)];
+          }
+          double* __restrict__ sg = ptrs.S[kk];
+#pragma unroll 1
+          for (int a = 0; a < nc; ++a)
+          {
+            const int fm = (info[a] >> 2) & 3, fp = (info[a] >> 4) & 3;
+            const bool rev0 = (info[a] & 64) != 0;
+            const int am = (a == 0) ? nc - 1 : a - 1;
+            const double p_ea = -pp[a];
+            const double p_em = rev0 ? -pp[am] : pm[a];
+            double um[K], up[K];
+#pragma unroll
+            for (int j = 0; j < k; ++j)
+            {
+              const int pd_m = (j == 0) ? 0 : a * (k - 1) + j;
+              const int pd_p = (j == 0) ? 0 : ((internal && a == nc - 1) ? 0 : (a + 1) * (k - 1)) + j;
+              um[j] = p_em * xcol[pd_m];
+              up[j] = p_ea * xcol[pd_p];
+            }
+            if (rev0)
+            {
+              double tmp[K];
+#pragma unroll
+              for (int i = 0; i < k; ++i)
+              {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < k; ++j)
+                  acc += t_trafo[j * k + i] * um[j];
+                tmp[i] = acc;
+              }
+#pragma unroll
+              for (int i = 0; i < k; ++i)
+                um[i] = tmp[i];
+            }
+            double* dst = sg + (size_t)cell[a] * nrt;
+#pragma unroll
+            for (int j = 0; j < k; ++j)
+            {
+              if (use_atomics)
+              {
+                atomicAdd(dst + fm * k + j, um[j]);
+                atomicAdd(dst + fp * k + j, up[j]);
+              }
+              else
+              {
+                dst[fm * k + j] += um[j];
+                dst[fp * k + j] += up[j];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < nadd; ++i)
+            {
+              const double val = xcol[nf * (k - 1) + 1 + a * nadd + i];
+              if (use_atomics)
+                atomicAdd(dst + 3 * k + ndiv + i, val);
+              else
+                dst[3 * k + ndiv + i] += val;
+            }
+          }
+        }
+      }
+    }
   }
 }
 
@@ -793,19 +1269,48 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   const int bs = 128;
   const size_t smem = (size_t)h->tv.ndoubles * sizeof(double);
   const bool atomics = (h->flags & EQLB_FLAG_ATOMIC) != 0;
-  auto kern8 = patch_kernel<K, NDG, 8, EV>;
-  auto kern16 = patch_kernel<K, NDG, EQLB_NCMAX, EV>;
-  auto kern = (h->ncmax <= 8) ? kern8 : kern16;
+  const bool stress = !EV && (h->flags & EQLB_FLAG_STRESS) != 0 && K >= 2;
+  constexpr bool CAN_STRESS = !EV && K >= 2 && K <= 3;
+  auto kern = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, false> : patch_kernel<K, NDG, EQLB_NCMAX, EV, false>;
+  if (stress)
+  {
+    if constexpr (CAN_STRESS)
+      kern = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, true> : patch_kernel<K, NDG, EQLB_NCMAX, EV, true>;
+    else
+      throw EqlbError(EQLB_ERR_INPUT, "stress equilibration: flux degree not supported by the CUDA kernel");
+  }
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int32_t* dgmap = h->dg_identity ? nullptr : h->d_dg_dofmap.p;
   const size_t bstride = (size_t)h->ncell * h->nrt;
+  if constexpr (CAN_STRESS)
+  {
+    // grouped boundary patches first, group by group in the reference's order
+    // (se/reconstruction.hpp:170-234): equilibrate all members without weak symmetry
+    // (they overlap -> atomics), then weak symmetry on the first member from the
+    // accumulated global stress
+    if (stress)
+      for (size_t g = 0; g + 1 < h->h_group_off.size(); ++g)
+      {
+        const int first = h->h_group_off[g], count = h->h_group_off[g + 1] - first;
+        auto kplain = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, false> : patch_kernel<K, NDG, EQLB_NCMAX, EV, false>;
+        CUDA_CHECK(cudaFuncSetAttribute(kplain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kplain<<<1, bs, smem, h->stream>>>(pv, first, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs, h->d_bflux.p, bstride,
+                                           1, h->d_cell_fct.p, h->nfct, 0);
+        CUDA_CHECK(cudaGetLastError());
+        kern<<<1, bs, smem, h->stream>>>(pv, first, 1, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs, h->d_bflux.p, bstride, 1,
+                                         h->d_cell_fct.p, h->nfct, 1);
+        CUDA_CHECK(cudaGetLastError());
+        h->launches += 2;
+      }
+  }
+  const int ngrouped = h->h_group_off.empty() ? 0 : h->h_group_off.back();
   if (atomics)
   {
-    const int count = h->nactive;
+    const int count = h->nactive - ngrouped;
     if (count == 0)
       return;
-    kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, 0, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
-                                                        h->d_bflux.p, bstride, 1, h->d_cell_fct.p, h->nfct);
+    kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, ngrouped, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
+                                                        h->d_bflux.p, bstride, 1, h->d_cell_fct.p, h->nfct, 0);
     CUDA_CHECK(cudaGetLastError());
     h->launches++;
   }
@@ -818,7 +1323,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       if (count == 0)
         continue;
       kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, first, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,
-                                                          h->d_bflux.p, bstride, 0, h->d_cell_fct.p, h->nfct);
+                                                          h->d_bflux.p, bstride, 0, h->d_cell_fct.p, h->nfct, 0);
       CUDA_CHECK(cudaGetLastError());
       h->launches++;
     }
@@ -861,8 +1366,9 @@ void dispatch(eqlb_handle* h, const double* const* dG, const double* const* dF, 
 
 void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn)
 {
-  (void)dKorn;
   dispatch<false>(h, dG, dF, dSigma);
+  if (dKorn)
+    launch_korn(h, dKorn);
 }
 
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)

@@ -288,3 +288,18 @@ class FluxEqlbEV(FluxEquilibrator):
 
     def equilibrate_fluxes(self):
         reconstruct_fluxes_minimisation(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs)
+
+
+def local_projection(problem: _Problem, qvals):
+    """`dolfinx_eqlb.lsolver.local_projection` (`lsolver/projection.py:17-77`) for DG_p
+    targets on affine cells: `qvals[i][cell*nq + q]` are the values of the i-th function at
+    the cell quadrature points; returns the DG_p coefficient vectors (CUDA)."""
+    lib = problem.lib
+    qv = _as_ptr_list(qvals)
+    T, m = problem.tables, problem.mesh
+    for q in qv:
+        if q.shape[0] != m.ncell * T.nq:
+            raise RuntimeError("local_projection: one value per cell quadrature point required")
+    out = [np.zeros(m.ncell * T.ndg) for _ in qv]
+    _check(lib, lib.eqlb_local_project(problem.h, len(qv), cabi.ptr_array(qv), cabi.ptr_array(out), 0))
+    return out

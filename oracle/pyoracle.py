@@ -189,3 +189,15 @@ def ev_patch_maps(mesh, tables, bc: BCData, node):
     _check(rc)
     out["ncells"] = int(nc[0])
     return out
+
+
+def local_project(mesh, tables, qvals):
+    """oracle of `local_projection` (lsolver/projection.py:17-77) into DG_p."""
+    pm, pt = PackedMesh(mesh, tables.ndg), PackedTables(tables)
+    L = lib()
+    L.oracle_local_project.restype = C.c_int
+    L.oracle_local_project.argtypes = [C.POINTER(EqlbMesh), C.POINTER(EqlbTables), C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+    qv = [np.ascontiguousarray(q, dtype=np.float64) for q in qvals]
+    out = [np.zeros(mesh.ncell * tables.ndg) for _ in qv]
+    _check(L.oracle_local_project(C.byref(pm.struct), C.byref(pt.struct), len(qv), ptr_array(qv), ptr_array(out)))
+    return out

@@ -1,0 +1,37 @@
+"""GPU parity of the cell-wise local projector (base/local_solver.hpp) via the C ABI."""
+
+import numpy as np
+import pytest
+
+from common import make_mesh
+from dolfinx_eqlb_b200 import eqlb, tables as tb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_local_projection_parity(k):
+    from oracle import pyoracle as po
+
+    m = make_mesh("crossed", 6, 3, perturb=0.3)
+    T = tb.make_tables(k)
+    rng = np.random.default_rng(2)
+    qv = [rng.standard_normal(m.ncell * T.nq) for _ in range(4)]  # 4 RHS at once (test_localsolver_multilhs.py)
+    ref = po.local_project(m, T, qv)
+    prob = eqlb._Problem(m, T, 1)
+    got = eqlb.local_projection(prob, qv)
+    for a, b in zip(got, ref):
+        assert np.abs(a - b).max() < 1e-12 * max(1.0, np.abs(b).max())
+
+
+def test_projection_reproduces_polynomials():
+    """Projecting a function of the space returns its coefficients (local == global projection
+    for DG, test_localsolver_projection.py)."""
+    m = make_mesh("crossed", 4, None)
+    T = tb.make_tables(3)
+    rng = np.random.default_rng(1)
+    coef = rng.standard_normal((m.ncell, T.ndg))
+    qv = (coef @ T.dg_q[0].T).ravel()
+    prob = eqlb._Problem(m, T, 1)
+    got = eqlb.local_projection(prob, [qv])[0]
+    assert np.abs(got - coef.ravel()).max() < 1e-12

@@ -84,9 +84,22 @@ void colour_patches(eqlb_handle* h)
     h->h_colour_off[c + 1] += h->h_colour_off[c];
   std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
   h->h_order.resize(h->nactive);
-  for (int z = 0; z < n; ++z)
-    if (h->h_owned[z] && !h->h_grouped[z])
-      h->h_order[pos[h->h_colour[z]]++] = z;
+  // within a colour: patches eligible for the streaming k=2 kernel first (interior patches,
+  // or any patch of a single-RHS problem: `reversion_required` cannot occur there)
+  auto eligible = [&](int z)
+  {
+    return h->nrhs == 1
+           || (h->h_node_fct_off[z + 1] - h->h_node_fct_off[z]) == (h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]);
+  };
+  h->h_colour_fast.assign(ncol, 0);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int z = 0; z < n; ++z)
+      if (h->h_owned[z] && !h->h_grouped[z] && eligible(z) == (pass == 0))
+      {
+        h->h_order[pos[h->h_colour[z]]++] = z;
+        if (pass == 0)
+          h->h_colour_fast[h->h_colour[z]]++;
+      }
 }
 
 void append(std::vector<double>& dst, const double* src, size_t n, int& offset)
@@ -272,6 +285,8 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
           h->d_proj.upload(P.data(), P.size());
         }
 
+        if (t->k == 2 && t->p == 1)
+          build_k2_tables(h.get(), t);
         launch_compute_cellJ(h.get());
         colour_patches(h.get());
         CUDA_CHECK(cudaStreamSynchronize(h->stream));

@@ -1318,8 +1318,16 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   {
     for (int c = 0; c < h->ncolours; ++c)
     {
-      const int first = h->h_colour_off[c];
-      const int count = h->h_colour_off[c + 1] - first;
+      int first = h->h_colour_off[c];
+      int count = h->h_colour_off[c + 1] - first;
+      if (K == 2 && NDG == 3 && !stress && h->d_k2tab.p && !(h->flags & EQLB_FLAG_GENERIC))
+      {
+        // streaming k=2 kernel for the eligible head of the colour, generic kernel for the rest
+        const int nfast = h->h_colour_fast[c];
+        launch_k2(h, EV, ptrs, first, nfast, 0);
+        first += nfast;
+        count -= nfast;
+      }
       if (count == 0)
         continue;
       kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, first, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs,

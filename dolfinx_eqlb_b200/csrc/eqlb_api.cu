@@ -92,13 +92,18 @@ void colour_patches(eqlb_handle* h)
            || (h->h_node_fct_off[z + 1] - h->h_node_fct_off[z]) == (h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]);
   };
   h->h_colour_fast.assign(ncol, 0);
+  h->h_colour_maxnf.assign(ncol, 0);
   for (int pass = 0; pass < 2; ++pass)
     for (int z = 0; z < n; ++z)
       if (h->h_owned[z] && !h->h_grouped[z] && eligible(z) == (pass == 0))
       {
         h->h_order[pos[h->h_colour[z]]++] = z;
         if (pass == 0)
+        {
           h->h_colour_fast[h->h_colour[z]]++;
+          h->h_colour_maxnf[h->h_colour[z]]
+              = std::max(h->h_colour_maxnf[h->h_colour[z]], h->h_node_fct_off[z + 1] - h->h_node_fct_off[z]);
+        }
       }
 }
 

@@ -563,6 +563,420 @@ patch_k2_kernel(PatchView pv, int first, int count, const double* __restrict__ k
 #undef ST
 }
 
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative variant: S lanes per patch, ONE LANE PER PATCH CELL.
+// ncu on the per-thread streaming kernel (profiles/README.md, round-1 second capture)
+// showed it latency bound: every thread walks its 8 cells through dependent global loads
+// (record -> J/G/f) with 8 warps/SM of occupancy (170 registers + 72 KB shared state per
+// CTA), issue slots 17 % busy.  Here all cells of a patch are loaded and turned into cell
+// tensors concurrently (32 independent load streams per warp), the explicit sweep becomes
+// a segmented inclusive scan, the bordered tridiagonal elimination runs along the lanes
+// with shuffles, and no per-thread state is left in shared or local memory.
+// S = 4, 8 or 16 >= number of patch facets of every patch of the launch.
+// ---------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ double seg_sum(double v)
+{
+#pragma unroll
+  for (int o = S / 2; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o, S);
+  return v;
+}
+
+template <bool EV, int S>
+__global__ void __launch_bounds__(128)
+patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ k2tab, const double* __restrict__ cellJ,
+                 int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
+                 const int32_t* __restrict__ cell_fct, int nfct)
+{
+  extern __shared__ double s_mem[];
+  double* s_blk = s_mem;
+  double* s_dgm = s_mem + 6 * K2_BLOCK;
+  double* s_mono = s_dgm + 9;
+  for (int i = threadIdx.x; i < K2_TAB; i += blockDim.x)
+    s_mem[i] = k2tab[i];
+  __syncthreads();
+
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int PPW = 32 / S;
+  constexpr int k = 2, nrt = 8;
+  const int lane = threadIdx.x & 31;
+  const int j = lane % S;  // cell index within the patch / owned chain facet
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int p = warp * PPW + lane / S;
+  const bool valid = p < count;
+  const size_t ip = (size_t)first + (valid ? p : 0);
+  const int nc = valid ? pv.ncells[ip] : 0;
+  const bool active = j < nc;
+  const int32_t c = active ? pv.cell[(size_t)j * pv.stride + ip] : 0;
+  const int info = active ? pv.info[(size_t)j * pv.stride + ip] : 0;
+  const int fm = (info >> 2) & 3, fp = active ? (info >> 4) & 3 : 1;
+  const bool rev0 = (info & 64) != 0, rev1 = (info & 128) != 0;
+  const bool first_c = (j == 0), last_c = (j == nc - 1);
+  const double* blk = s_blk + combo_of(fm, fp) * K2_BLOCK;
+
+  for (int r = 0; r < nrhs; ++r)
+  {
+    const double* __restrict__ G = ptrs.G[r];
+    const double* __restrict__ Fv = ptrs.F[r];
+    double* __restrict__ sig = ptrs.S[r];
+    const uint8_t ri = valid ? pv.rhsinfo[(size_t)r * pv.stride + ip] : 0;
+    const int ptype = ri & 3;
+    const bool bc_e0 = (ri & 8) != 0, bc_en = (ri & 16) != 0;
+    const bool internal = (ptype == EQLB_PATCH_INTERNAL);
+    const bool req_bc = (ptype == EQLB_PATCH_ESSNT_DUAL || ptype == EQLB_PATCH_MIXED);
+    const bool mark_z = req_bc, mark_f0 = req_bc, mark_fn = (ptype == EQLB_PATCH_ESSNT_DUAL);
+    const int nch = internal ? nc - 1 : nc;
+
+    K2Cell cur;
+    if (active)
+      load_cell<EV>(cur, c, info, cellJ, G, Fv, s_blk, s_dgm);
+    else
+    {
+      cur.det = 1.0;
+      cur.pm = cur.pp = 0.0;
+      cur.cm[0] = cur.cm[1] = cur.cm[2] = 0.0;
+      cur.mm[0] = cur.mm[1] = cur.mp[0] = cur.mp[1] = 0.0;
+      cur.g[0] = cur.g[1] = cur.g[2] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        cur.adj[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        cur.G[i] = 0.0;
+    }
+    const double sgn = cur.det > 0.0 ? 1.0 : -1.0;
+
+    const bool on_bnd = active && !internal && (first_c || last_c);
+    bool has_bc = false;
+    if (on_bnd)
+    {
+      if (ptype == EQLB_PATCH_ESSNT_DUAL)
+        has_bc = true;
+      else if (ptype == EQLB_PATCH_MIXED)
+        has_bc = first_c ? bc_e0 : bc_en;
+    }
+    double bv0 = 0.0, bv1 = 0.0;
+    if (has_bc)
+      patch_bc(bflux + (size_t)r * bflux_stride + (size_t)c * nrt + (first_c ? fm : fp) * k, blk + K2_O_BC + (first_c ? 0 : 4),
+               bv0, bv1);
+    // a 2-cell... every boundary patch has nc >= 2, so first and last cell are different lanes
+
+    // ---- EV: mean-value shift (ev/assembly.hpp:283-298) ----
+    if (EV)
+    {
+      double tot = active ? sgn * cur.cm[0] : 0.0;
+      if (has_bc && ptype == EQLB_PATCH_ESSNT_DUAL)
+        tot -= (first_c ? cur.pm : cur.pp) * bv0;
+      tot = seg_sum<S>(tot);
+      const double area2 = seg_sum<S>(active ? fabs(cur.det) : 0.0);
+      if (valid && (internal || ptype == EQLB_PATCH_ESSNT_DUAL))
+      {
+        const double lam = tot / (0.5 * area2);
+#pragma unroll
+        for (int t = 0; t < K2_NT; ++t)
+          cur.cm[t] -= lam * cur.det * s_mono[t];
+      }
+    }
+
+    // ---- neighbours along the fan ----
+    double pp_prev = __shfl_up_sync(FULL, cur.pp, 1, S);
+    double mp0_prev = __shfl_up_sync(FULL, cur.mp[0], 1, S);
+    const double pp_last = __shfl_sync(FULL, cur.pp, max(nc - 1, 0), S);
+    if (first_c)
+    {
+      pp_prev = internal ? pp_last : 0.0;
+      mp0_prev = 0.0;
+    }
+    double n_pm = __shfl_down_sync(FULL, cur.pm, 1, S);
+    double n_m0 = __shfl_down_sync(FULL, cur.mm[0], 1, S);
+    double n_m1 = __shfl_down_sync(FULL, cur.mm[1], 1, S);
+    const double f_pm = __shfl_sync(FULL, cur.pm, 0, S), f_m0 = __shfl_sync(FULL, cur.mm[0], 0, S),
+                 f_m1 = __shfl_sync(FULL, cur.mm[1], 0, S);
+    if (last_c)
+    {
+      n_pm = f_pm;
+      n_m0 = f_m0;
+      n_m1 = f_m1;
+    }
+
+    // ---- step 1 as a segmented scan: c+_a = sum_{b<=a} (vol_b - t_b), c-_a = vol_a - c+_a ----
+    double cfv[6] = {0.0, 0.0, 0.0, 0.0, cur.cm[1], cur.cm[2]};
+    double surf = 0.0;
+    if (!EV && active)
+    {
+      if (!first_c)
+        surf = -cur.mm[0] - pp_prev * cur.pm * mp0_prev;
+      else if (!internal && (has_bc || ptype == EQLB_PATCH_MIXED))
+      {
+        cfv[1] += ((ptype == EQLB_PATCH_MIXED && !has_bc) ? 1.0 : -1.0) * cur.mm[1];
+        if (has_bc)
+          surf = -cur.mm[0];
+      }
+    }
+    const double vol = active ? sgn * cur.cm[0] : 0.0;
+    const double t_add = cur.pm * surf + ((has_bc && first_c) ? cur.pm * bv0 : 0.0);
+    double c_p = vol - t_add;
+#pragma unroll
+    for (int o = 1; o < S; o <<= 1)
+    {
+      const double up = __shfl_up_sync(FULL, c_p, o, S);
+      if (j >= o)
+        c_p += up;
+    }
+    const double c_m = vol - c_p;
+    if (has_bc)
+    {
+      if (first_c)
+        cfv[1] += bv1;
+      else
+        cfv[3] += bv1;
+    }
+    if (active)
+    {
+      if (!EV)
+      {
+        if (on_bnd && last_c)
+          cfv[3] += (has_bc ? -1.0 : 1.0) * cur.mp[1];
+        else
+        {
+          const double tau = -cur.pp * n_pm;
+          const double mt1 = rev1 ? (n_m0 - n_m1) : n_m1;
+          double h = tau * mt1 - cur.mp[1];
+          if (rev1 && !last_c)
+            h += -(tau * n_m0 - cur.mp[0]) + n_pm * c_p;
+          cfv[3] += h;
+        }
+      }
+      else if (rev1 && !last_c)
+        cfv[3] += n_pm * c_p;
+      cfv[0] += cur.pm * c_m;
+      cfv[2] += cur.pp * c_p;
+    }
+
+    // ---- cell block of the RT mass matrix and load ----
+    double MB[4][6];
+    {
+      const double* tm = blk + K2_O_MASS;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int s2 = 0; s2 < 6; ++s2)
+          MB[q][s2] = cur.g[0] * tm[q * 6 + s2] + cur.g[1] * tm[24 + q * 6 + s2] + cur.g[2] * tm[48 + q * 6 + s2];
+    }
+    double y[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+    {
+      double s2 = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2)
+        s2 += MB[q][c2] * cfv[c2];
+      y[q] = s2;
+    }
+    if (EV)
+    {
+      const double* hh = blk + K2_O_H;
+#pragma unroll
+      for (int mI = 0; mI < 3; ++mI)
+      {
+        const double gx = cur.G[2 * mI], gy = cur.G[2 * mI + 1];
+        const double jg0 = sgn * (cur.adj[3] * gx - cur.adj[2] * gy);
+        const double jg1 = sgn * (-cur.adj[1] * gx + cur.adj[0] * gy);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          y[q] -= jg0 * hh[(mI * 4 + q) * 2] + jg1 * hh[(mI * 4 + q) * 2 + 1];
+      }
+    }
+    if (rev0)
+    {
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2)
+        MB[0][s2] = -MB[0][s2] - MB[1][s2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        MB[q][0] = -MB[q][0] - MB[q][1];
+      y[0] = -y[0] - y[1];
+    }
+    const double p_ea = -cur.pp;
+    const double p_em = rev0 ? -pp_prev : cur.pm;
+    const double pe = p_em * p_ea;
+    const bool hi_is_F = active && internal && last_c;
+    const bool m_lo = first_c ? mark_f0 : false;
+    const bool m_hi = (!internal && last_c) ? mark_fn : false;
+    double T00 = MB[1][1], T22 = MB[3][3], T02 = pe * MB[1][3];
+    double T11 = MB[0][0] + MB[2][2] + 2.0 * pe * MB[0][2];
+    double T01 = MB[1][0] + pe * MB[1][2], T12 = pe * MB[3][0] + MB[3][2];
+    double l0 = -p_em * y[1], l1 = -(p_em * y[0] + p_ea * y[2]), l2 = -p_ea * y[3];
+    if (m_lo)
+      T00 = T01 = T02 = l0 = 0.0;
+    if (m_hi)
+      T22 = T12 = T02 = l2 = 0.0;
+    if (mark_z)
+      T11 = T01 = T12 = l1 = 0.0;
+    if (!active)
+      T00 = T22 = T02 = T11 = T01 = T12 = l0 = l1 = l2 = 0.0;
+
+    // ---- patch system: lane b owns chain facet E_b (1 <= b <= nch); E_0 and d0 are the border ----
+    const bool hi_chain = active && !hi_is_F;
+    const double up22 = __shfl_up_sync(FULL, hi_chain ? T22 : 0.0, 1, S);
+    const double up12 = __shfl_up_sync(FULL, hi_chain ? T12 : 0.0, 1, S);
+    const double upl2 = __shfl_up_sync(FULL, hi_chain ? l2 : 0.0, 1, S);
+    const double up02 = __shfl_up_sync(FULL, T02, 1, S);  // coupling (E_0, E_1) from cell 0
+    const bool owns = (j >= 1 && j <= nch);
+    double D = 1.0, e = 0.0, g = 0.0, w = 0.0, l = 0.0;
+    if (owns)
+    {
+      D = T00 + up22;
+      w = T01 + up12;
+      l = l0 + upl2;
+      g = (j == 1 ? up02 : 0.0) + (hi_is_F ? T02 : 0.0);
+      e = (hi_chain && j < nch) ? T02 : 0.0;
+      if (!internal && j == nc && mark_fn)
+      {
+        D = 1.0;
+        g = w = l = 0.0;
+      }
+    }
+    // border parts held by this lane
+    double bFF = (first_c ? T00 : 0.0) + (hi_is_F ? T22 : 0.0);
+    double bFZ = (first_c ? T01 : 0.0) + (hi_is_F ? T12 : 0.0);
+    double bLF = (first_c ? l0 : 0.0) + (hi_is_F ? l2 : 0.0);
+    double bZZ = T11, bLZ = l1;
+
+    double ipv = 1.0;
+    double oD = 0.0, oG = 0.0, oW = 0.0, oL = 0.0;
+#pragma unroll
+    for (int b = 1; b < S; ++b)
+    {
+      const double rD = __shfl_up_sync(FULL, oD, 1, S), rG = __shfl_up_sync(FULL, oG, 1, S),
+                   rW = __shfl_up_sync(FULL, oW, 1, S), rL = __shfl_up_sync(FULL, oL, 1, S);
+      if (j == b)
+      {
+        D -= rD;
+        g -= rG;
+        w -= rW;
+        l -= rL;
+        ipv = 1.0 / D;
+        const double ei = e * ipv, gi = g * ipv, wi = w * ipv;
+        oD = ei * e;
+        oG = ei * g;
+        oW = ei * w;
+        oL = ei * l;
+        bFF -= gi * g;
+        bFZ -= gi * w;
+        bZZ -= wi * w;
+        bLF -= gi * l;
+        bLZ -= wi * l;
+      }
+    }
+    double S_FF = seg_sum<S>(bFF), S_FZ = seg_sum<S>(bFZ), S_ZZ = seg_sum<S>(bZZ);
+    const double l_F = seg_sum<S>(bLF), l_Z = seg_sum<S>(bLZ);
+    if (mark_z)
+      S_ZZ = 1.0;
+    if (mark_f0)
+      S_FF = 1.0;
+    double u_F = 0.0, u_Z = 0.0;
+    if (valid)
+    {
+      const double idet = 1.0 / (S_FF * S_ZZ - S_FZ * S_FZ);
+      u_F = (l_F * S_ZZ - S_FZ * l_Z) * idet;
+      u_Z = (S_FF * l_Z - S_FZ * l_F) * idet;
+    }
+    double u = 0.0;
+#pragma unroll
+    for (int b = S - 1; b >= 1; --b)
+    {
+      const double un = __shfl_down_sync(FULL, u, 1, S);
+      if (j == b)
+        u = (l - e * un - g * u_F - w * u_Z) * ipv;
+    }
+    const double u_next = __shfl_down_sync(FULL, u, 1, S);
+
+    // ---- map back and accumulate ----
+    if (active)
+    {
+      const double u_lo = first_c ? u_F : u;
+      const double u_hi = hi_is_F ? u_F : u_next;
+      double um0 = p_em * u_Z, um1 = p_em * u_lo;
+      if (rev0)
+      {
+        const double t0 = -um0, t1 = -um0 + um1;
+        um0 = t0;
+        um1 = t1;
+      }
+      const double up0 = p_ea * u_Z, up1 = p_ea * u_hi;
+      const double clo0 = cfv[0] + um0, clo1 = cfv[1] + um1;
+      const double chi0 = cfv[2] + up0, chi1 = cfv[3] + up1;
+      if (EV)
+      {
+        for (int side = (first_c && !internal) ? 0 : 1; side < 2; ++side)
+        {
+          const int fl = side ? fp : fm;
+          const bool refl = (info & (side ? 512 : 256)) != 0;
+          const double cl0 = side ? chi0 : clo0, cl1 = side ? chi1 : clo1;
+          const double cg0 = refl ? -cl0 : cl0;
+          const double cg1 = refl ? (-cl0 + cl1) : cl1;
+          double* d = sig + (size_t)cell_fct[3 * (size_t)c + fl] * k;
+          if (use_atomics)
+          {
+            atomicAdd(d, cg0);
+            atomicAdd(d + 1, cg1);
+          }
+          else
+          {
+            double2 vv = *reinterpret_cast<double2*>(d);
+            vv.x += cg0;
+            vv.y += cg1;
+            *reinterpret_cast<double2*>(d) = vv;
+          }
+        }
+        double* dstc = sig + (size_t)nfct * k + (size_t)c * 2;
+        if (use_atomics)
+        {
+          atomicAdd(dstc, cfv[4]);
+          atomicAdd(dstc + 1, cfv[5]);
+        }
+        else
+        {
+          double2 vv = *reinterpret_cast<double2*>(dstc);
+          vv.x += cfv[4];
+          vv.y += cfv[5];
+          *reinterpret_cast<double2*>(dstc) = vv;
+        }
+      }
+      else
+      {
+        double* d = sig + (size_t)c * nrt;
+        if (use_atomics)
+        {
+          atomicAdd(d + fm * 2, clo0);
+          atomicAdd(d + fm * 2 + 1, clo1);
+          atomicAdd(d + fp * 2, chi0);
+          atomicAdd(d + fp * 2 + 1, chi1);
+          atomicAdd(d + 6, cfv[4]);
+          atomicAdd(d + 7, cfv[5]);
+        }
+        else
+        {
+          double2* d2 = reinterpret_cast<double2*>(d);
+          double2 vlo = d2[fm], vhi = d2[fp], vdv = d2[3];
+          vlo.x += clo0;
+          vlo.y += clo1;
+          vhi.x += chi0;
+          vhi.y += chi1;
+          vdv.x += cfv[4];
+          vdv.y += cfv[5];
+          d2[fm] = vlo;
+          d2[fp] = vhi;
+          d2[3] = vdv;
+        }
+      }
+    }
+  }
+}
+
 } // namespace
 
 // gather the reference tables per local facet pair (fm, fp); v = 3 - fm - fp
@@ -613,25 +1027,40 @@ void build_k2_tables(eqlb_handle* h, const eqlb_tables* t)
 }
 
 template <bool EV>
-static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics)
+static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf)
 {
   if (count <= 0)
     return;
   const int bs = 128;
-  const size_t smem = ((size_t)K2_TAB + (size_t)K2_SLOTS * h->ncmax * bs) * sizeof(double);
-  auto kern = patch_k2_kernel<EV>;
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(h->patch_view(), first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs,
-                                                      h->d_bflux.p, (size_t)h->ncell * h->nrt, use_atomics, h->d_cell_fct.p,
-                                                      h->nfct);
+  const PatchView pv = h->patch_view();
+  const size_t bstride = (size_t)h->ncell * h->nrt;
+  if (maxnf <= 16 && !(h->flags & EQLB_FLAG_K2_THREAD))
+  {
+    // warp-cooperative kernel: S lanes per patch
+    const size_t smem = (size_t)K2_TAB * sizeof(double);
+    const int S = maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16);
+    const int ppb = bs / S;  // patches per block
+    const int grid = (count + ppb - 1) / ppb;
+    auto kern = (S == 4) ? patch_k2w_kernel<EV, 4> : (S == 8 ? patch_k2w_kernel<EV, 8> : patch_k2w_kernel<EV, 16>);
+    kern<<<grid, bs, smem, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p, bstride,
+                                        use_atomics, h->d_cell_fct.p, h->nfct);
+  }
+  else
+  {
+    const size_t smem = ((size_t)K2_TAB + (size_t)K2_SLOTS * h->ncmax * bs) * sizeof(double);
+    auto kern = patch_k2_kernel<EV>;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs,
+                                                        h->d_bflux.p, bstride, use_atomics, h->d_cell_fct.p, h->nfct);
+  }
   CUDA_CHECK(cudaGetLastError());
   h->launches++;
 }
 
-void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics)
+void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf)
 {
   if (ev)
-    launch_k2_range<true>(h, ptrs, first, count, use_atomics);
+    launch_k2_range<true>(h, ptrs, first, count, use_atomics, maxnf);
   else
-    launch_k2_range<false>(h, ptrs, first, count, use_atomics);
+    launch_k2_range<false>(h, ptrs, first, count, use_atomics, maxnf);
 }

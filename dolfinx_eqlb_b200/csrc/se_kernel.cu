@@ -1324,7 +1324,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       {
         // streaming k=2 kernel for the eligible head of the colour, generic kernel for the rest
         const int nfast = h->h_colour_fast[c];
-        launch_k2(h, EV, ptrs, first, nfast, 0);
+        launch_k2(h, EV, ptrs, first, nfast, 0, h->h_colour_maxnf[c]);
         first += nfast;
         count -= nfast;
       }

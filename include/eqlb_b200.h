@@ -41,6 +41,7 @@ extern "C" {
 #define EQLB_FLAG_STRESS 1u   /* first gdim fluxes are rows of a stress tensor (weak symmetry) */
 #define EQLB_FLAG_ATOMIC 2u   /* accumulate with fp64 atomics instead of colour-ordered launches */
 #define EQLB_FLAG_GENERIC 4u  /* always use the generic patch kernel (no degree-2 streaming kernel) */
+#define EQLB_FLAG_K2_THREAD 8u /* degree 2: thread-per-patch streaming kernel instead of lane-per-cell */
 
 /* wire values, `base/Patch.hpp:20-33` */
 enum eqlb_patch_type { EQLB_PATCH_INTERNAL = 0, EQLB_PATCH_ESSNT_DUAL = 1,

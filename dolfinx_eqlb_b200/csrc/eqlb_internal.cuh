@@ -185,6 +185,7 @@ struct eqlb_handle
   DevBuf<double> d_k2tab;             // gathered tables of the k=2 streaming kernel
   std::vector<int32_t> h_colour;      // [nnode]
   int ncolours = 0;
+  int nseg = 0;  // launch segments = spatial chunks x colours (h_colour_* arrays are per segment)
   size_t pstride = 0;
   DevBuf<int32_t> d_pnode, d_pcell;
   DevBuf<uint8_t> d_pncells, d_prhs;

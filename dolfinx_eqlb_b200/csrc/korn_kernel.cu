@@ -151,7 +151,7 @@ void launch_korn(eqlb_handle* h, double* dKorn)
     }
     return;
   }
-  for (int c = 0; c < h->ncolours; ++c)
+  for (int c = 0; c < h->nseg; ++c)
   {
     const int first = h->h_colour_off[c], count = h->h_colour_off[c + 1] - first;
     if (count == 0)

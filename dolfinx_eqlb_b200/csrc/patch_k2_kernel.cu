@@ -27,7 +27,9 @@ namespace
 constexpr int K2_NT = 3;  // cell moments: (0,0), (0,1), (1,0)
 // per-combo table block (doubles): mass [3][4][6], H [3][4][2], cmf [3][3], cmg [3][3][2],
 // fmom [2 sides][2][3], bc [2 sides][2][2]
-constexpr int K2_O_MASS = 0, K2_O_H = 72, K2_O_CMF = 96, K2_O_CMG = 105, K2_O_FM = 123, K2_O_BC = 135, K2_BLOCK = 144;
+// (block stride 146: consecutive combos are 4 banks apart -> lanes working on different
+//  local facet pairs read their tables without shared-memory bank conflicts, 16-B aligned)
+constexpr int K2_O_MASS = 0, K2_O_H = 72, K2_O_CMF = 96, K2_O_CMG = 106, K2_O_FM = 124, K2_O_BC = 136, K2_BLOCK = 146;
 constexpr int K2_TAB = 6 * K2_BLOCK + 12;  // + dg_mono [3][3] + mono_int [3]
 constexpr int K2_SLOTS = 8;                // per patch cell: ip,e,g,w,l of chain facet a+1 ; cz_m, cz_p, ch of cell a
 
@@ -585,7 +587,7 @@ __device__ __forceinline__ double seg_sum(double v)
 }
 
 template <bool EV, int S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ k2tab, const double* __restrict__ cellJ,
                  int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
                  const int32_t* __restrict__ cell_fct, int nfct)
@@ -758,12 +760,16 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
     // ---- cell block of the RT mass matrix and load ----
     double MB[4][6];
     {
-      const double* tm = blk + K2_O_MASS;
+      const double2* tm = reinterpret_cast<const double2*>(blk + K2_O_MASS);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int s2 = 0; s2 < 6; ++s2)
-          MB[q][s2] = cur.g[0] * tm[q * 6 + s2] + cur.g[1] * tm[24 + q * 6 + s2] + cur.g[2] * tm[48 + q * 6 + s2];
+        for (int s2 = 0; s2 < 3; ++s2)
+        {
+          const double2 a0 = tm[q * 3 + s2], a1 = tm[12 + q * 3 + s2], a2 = tm[24 + q * 3 + s2];
+          MB[q][2 * s2] = cur.g[0] * a0.x + cur.g[1] * a1.x + cur.g[2] * a2.x;
+          MB[q][2 * s2 + 1] = cur.g[0] * a0.y + cur.g[1] * a1.y + cur.g[2] * a2.y;
+        }
     }
     double y[4];
 #pragma unroll
@@ -777,7 +783,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
     }
     if (EV)
     {
-      const double* hh = blk + K2_O_H;
+      const double2* hh = reinterpret_cast<const double2*>(blk + K2_O_H);
 #pragma unroll
       for (int mI = 0; mI < 3; ++mI)
       {
@@ -786,7 +792,10 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
         const double jg1 = sgn * (-cur.adj[1] * gx + cur.adj[0] * gy);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          y[q] -= jg0 * hh[(mI * 4 + q) * 2] + jg1 * hh[(mI * 4 + q) * 2 + 1];
+        {
+          const double2 hv = hh[mI * 4 + q];
+          y[q] -= jg0 * hv.x + jg1 * hv.y;
+        }
       }
     }
     if (rev0)

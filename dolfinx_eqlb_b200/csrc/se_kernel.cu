@@ -1316,7 +1316,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   }
   else
   {
-    for (int c = 0; c < h->ncolours; ++c)
+    for (int c = 0; c < h->nseg; ++c)
     {
       int first = h->h_colour_off[c];
       int count = h->h_colour_off[c + 1] - first;

@@ -306,6 +306,8 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
 
         if (t->k == 2 && t->p == 1)
           build_k2_tables(h.get(), t);
+        if (kw_supported(t->k, t->ndg))
+          build_kw_tables(h.get(), t);
         launch_compute_cellJ(h.get());
         colour_patches(h.get());
         CUDA_CHECK(cudaStreamSynchronize(h->stream));

@@ -15,6 +15,7 @@
 //  * the patch system (SPD, hz <= 1+(k-1) n_f + nadd n_c) is factorised by an
 //    in-thread Cholesky.
 #include <cstdio>
+#include <cstdlib>
 
 #include "eqlb_internal.cuh"
 
@@ -1320,11 +1321,16 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
     {
       int first = h->h_colour_off[c];
       int count = h->h_colour_off[c + 1] - first;
-      if (K == 2 && NDG == 3 && !stress && h->d_k2tab.p && !(h->flags & EQLB_FLAG_GENERIC))
+      if (!stress && !(h->flags & EQLB_FLAG_GENERIC) && h->h_colour_maxnf[c] <= 16
+          && ((K == 2 && NDG == 3 && h->d_k2tab.p) || (kw_supported(K, NDG) && h->d_kwtab.p)))
       {
-        // streaming k=2 kernel for the eligible head of the colour, generic kernel for the rest
+        // specialised kernels for the eligible head of the segment, generic kernel for the rest
+        static const bool force_kw = getenv("EQLB_KW") != nullptr;
         const int nfast = h->h_colour_fast[c];
-        launch_k2(h, EV, ptrs, first, nfast, 0, h->h_colour_maxnf[c]);
+        if (K == 2 && !force_kw)
+          launch_k2(h, EV, ptrs, first, nfast, 0, h->h_colour_maxnf[c]);
+        else
+          launch_kw(h, EV, ptrs, first, nfast, 0, h->h_colour_maxnf[c]);
         first += nfast;
         count -= nfast;
       }

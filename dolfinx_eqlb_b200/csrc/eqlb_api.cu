@@ -422,6 +422,32 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
         h->d_prhs.alloc(h->pstride * h->nrhs);
         h->d_pcell.zero(h->stream);
         h->d_pinfo.zero(h->stream);
+        {
+          // lane records: S lanes per patch for the eligible head of every segment, each
+          // segment padded to a whole number of warps (zero records: ncells = 0)
+          h->h_seg_recoff.assign(h->nseg, -1);
+          h->h_seg_lanes.assign(h->nseg, 0);
+          std::vector<int64_t> seginfo(4 * (size_t)std::max(h->nseg, 1), 0);
+          int64_t nrec = 0;
+          for (int sg = 0; sg < h->nseg; ++sg)
+          {
+            const int maxnf = h->h_colour_maxnf[sg], nfast = h->h_colour_fast[sg];
+            const int lanes = (nfast == 0 || maxnf > 16) ? 0 : (maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16));
+            seginfo[4 * sg] = h->h_colour_off[sg];
+            seginfo[4 * sg + 1] = nfast;
+            seginfo[4 * sg + 2] = lanes;
+            seginfo[4 * sg + 3] = nrec;
+            if (lanes)
+            {
+              h->h_seg_recoff[sg] = nrec;
+              h->h_seg_lanes[sg] = lanes;
+              nrec += ((int64_t)nfast * lanes + 127) / 128 * 128;
+            }
+          }
+          h->d_prec.alloc((size_t)std::max<int64_t>(nrec, 128));
+          h->d_prec.zero(h->stream);
+          h->d_seginfo.upload(seginfo.data(), seginfo.size());
+        }
         launch_patch_builder(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         h->bcs_set = true;
       });

@@ -134,6 +134,12 @@ struct PatchView
   const int32_t* cell;   // [ncmax][stride]
   const uint16_t* info;  // [ncmax][stride]
   const uint8_t* rhsinfo; // [nrhs][stride]
+  // Lane records of the warp-cooperative kernels: one int4 per (patch, lane) with a
+  // fixed number S of lanes per patch inside a launch segment, so that a warp reads 512
+  // contiguous bytes and no load depends on another record load.
+  // x = cell, y = info | ncells << 16, z = global facet E_{a-1}, w = global facet E_a
+  // (lanes >= ncells: x = z = w = 0, info = 0).
+  const int4* rec;
 };
 
 struct eqlb_handle
@@ -191,6 +197,10 @@ struct eqlb_handle
   DevBuf<int32_t> d_pnode, d_pcell;
   DevBuf<uint8_t> d_pncells, d_prhs;
   DevBuf<uint16_t> d_pinfo;
+  DevBuf<int4> d_prec;                  // lane records of the eligible head of every segment
+  std::vector<int64_t> h_seg_recoff;    // [nseg] offset of the segment in d_prec (-1: none)
+  std::vector<int32_t> h_seg_lanes;     // [nseg] lanes per patch (4, 8, 16; 0: none)
+  DevBuf<int64_t> d_seginfo;            // [nseg][4] first, nfast, lanes, recoff
 
   // staging buffers for host-pointer calls
   DevBuf<double> d_stage_G, d_stage_f, d_stage_sigma, d_stage_korn;
@@ -211,5 +221,6 @@ void launch_korn(eqlb_handle* h, double* dKorn);
 void build_k2_tables(eqlb_handle* h, const eqlb_tables* t);
 bool kw_supported(int k, int ndg);
 void build_kw_tables(eqlb_handle* h, const eqlb_tables* t);
-void launch_kw(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf);
-void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf);
+void launch_kw(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff);
+void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf, int lanes,
+               int64_t recoff);

@@ -184,7 +184,8 @@ __global__ void patch_builder_kernel(MeshView m, const int8_t* __restrict__ face
                                      // compact records (colour order)
                                      int32_t* __restrict__ pnode, uint8_t* __restrict__ pncells,
                                      int32_t* __restrict__ pcell, uint16_t* __restrict__ pinfo,
-                                     uint8_t* __restrict__ prhs,
+                                     uint8_t* __restrict__ prhs, int4* __restrict__ prec,
+                                     const int64_t* __restrict__ seginfo, int nseg,
                                      // expanded, reference layout (node order); may be null
                                      int32_t* __restrict__ x_ncells, int32_t* __restrict__ x_cells,
                                      int32_t* __restrict__ x_fcts, int8_t* __restrict__ x_inod,
@@ -221,6 +222,34 @@ __global__ void patch_builder_kernel(MeshView m, const int8_t* __restrict__ face
     {
       x_rev[((size_t)node * ncmax + (a - 1)) * 2] = r0;
       x_rev[((size_t)node * ncmax + (a - 1)) * 2 + 1] = r1;
+    }
+  }
+  if (prec)
+  {
+    // lane records of the warp-cooperative kernels (only for the eligible head of a segment)
+    for (int sg = 0; sg < nseg; ++sg)
+    {
+      const int64_t first = seginfo[4 * sg], nfast = seginfo[4 * sg + 1], lanes = seginfo[4 * sg + 2];
+      if (lanes == 0 || i < first || i >= first + nfast)
+        continue;
+      int4* dst = prec + seginfo[4 * sg + 3] + (i - first) * lanes;
+      for (int a = 1; a <= (int)lanes; ++a)
+      {
+        int4 rc = make_int4(0, nc << 16, 0, 0);
+        if (a <= nc)
+        {
+          bool r0, r1;
+          reversed_flags(m, F, a, r0, r1);
+          const int rho_m = m.fct_perms[3 * F.cells[a] + F.fl[2 * a - 1]] ? 256 : 0;
+          const int rho_p = m.fct_perms[3 * F.cells[a] + F.fl[2 * a]] ? 512 : 0;
+          rc.x = F.cells[a];
+          rc.y |= F.inod[a] | (F.fl[2 * a - 1] << 2) | (F.fl[2 * a] << 4) | (r0 ? 64 : 0) | (r1 ? 128 : 0) | rho_m | rho_p;
+          rc.z = F.fcts[a - 1];
+          rc.w = F.fcts[a];
+        }
+        dst[a - 1] = rc;
+      }
+      break;
     }
   }
   int8_t type_prev = 0;
@@ -517,6 +546,7 @@ PatchView eqlb_handle::patch_view() const
   v.cell = d_pcell.p;
   v.info = d_pinfo.p;
   v.rhsinfo = d_prhs.p;
+  v.rec = d_prec.p;
   return v;
 }
 
@@ -541,7 +571,7 @@ void launch_patch_builder(eqlb_handle* h, int32_t* x_ncells, int32_t* x_cells, i
   patch_builder_kernel<<<(h->nactive + bs - 1) / bs, bs, 0, h->stream>>>(
       h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nactive, h->pstride, h->ncmax,
       expand ? nullptr : h->d_pnode.p, h->d_pncells.p, expand ? nullptr : h->d_pcell.p, h->d_pinfo.p,
-      expand ? nullptr : h->d_prhs.p, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
+      expand ? nullptr : h->d_prhs.p, expand ? nullptr : h->d_prec.p, h->d_seginfo.p, h->nseg, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->launches++;

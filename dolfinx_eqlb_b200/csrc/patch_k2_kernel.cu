@@ -590,7 +590,7 @@ template <bool EV, int S>
 __global__ void __launch_bounds__(128, 4)
 patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ k2tab, const double* __restrict__ cellJ,
                  int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
-                 const int32_t* __restrict__ cell_fct, int nfct)
+                 const int4* __restrict__ rec, int nfct)
 {
   extern __shared__ double s_mem[];
   double* s_blk = s_mem;
@@ -609,10 +609,12 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
   const int p = warp * PPW + lane / S;
   const bool valid = p < count;
   const size_t ip = (size_t)first + (valid ? p : 0);
-  const int nc = valid ? pv.ncells[ip] : 0;
+  // one coalesced 16-byte record per lane (segments are padded with zero records)
+  const int4 rc = rec[(size_t)warp * 32 + lane];
+  const int nc = valid ? (rc.y >> 16) : 0;
   const bool active = j < nc;
-  const int32_t c = active ? pv.cell[(size_t)j * pv.stride + ip] : 0;
-  const int info = active ? pv.info[(size_t)j * pv.stride + ip] : 0;
+  const int32_t c = rc.x;
+  const int info = active ? (rc.y & 0xffff) : 0;
   const int fm = (info >> 2) & 3, fp = active ? (info >> 4) & 3 : 1;
   const bool rev0 = (info & 64) != 0, rev1 = (info & 128) != 0;
   const bool first_c = (j == 0), last_c = (j == nc - 1);
@@ -922,12 +924,11 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       {
         for (int side = (first_c && !internal) ? 0 : 1; side < 2; ++side)
         {
-          const int fl = side ? fp : fm;
           const bool refl = (info & (side ? 512 : 256)) != 0;
           const double cl0 = side ? chi0 : clo0, cl1 = side ? chi1 : clo1;
           const double cg0 = refl ? -cl0 : cl0;
           const double cg1 = refl ? (-cl0 + cl1) : cl1;
-          double* d = sig + (size_t)cell_fct[3 * (size_t)c + fl] * k;
+          double* d = sig + (size_t)(side ? rc.w : rc.z) * k;
           if (use_atomics)
           {
             atomicAdd(d, cg0);
@@ -1036,23 +1037,24 @@ void build_k2_tables(eqlb_handle* h, const eqlb_tables* t)
 }
 
 template <bool EV>
-static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf)
+static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf, int lanes,
+                            int64_t recoff)
 {
   if (count <= 0)
     return;
   const int bs = 128;
   const PatchView pv = h->patch_view();
   const size_t bstride = (size_t)h->ncell * h->nrt;
-  if (maxnf <= 16 && !(h->flags & EQLB_FLAG_K2_THREAD))
+  if (lanes > 0 && recoff >= 0 && !(h->flags & EQLB_FLAG_K2_THREAD))
   {
     // warp-cooperative kernel: S lanes per patch
     const size_t smem = (size_t)K2_TAB * sizeof(double);
-    const int S = maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16);
+    const int S = lanes;
     const int ppb = bs / S;  // patches per block
     const int grid = (count + ppb - 1) / ppb;
     auto kern = (S == 4) ? patch_k2w_kernel<EV, 4> : (S == 8 ? patch_k2w_kernel<EV, 8> : patch_k2w_kernel<EV, 16>);
     kern<<<grid, bs, smem, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p, bstride,
-                                        use_atomics, h->d_cell_fct.p, h->nfct);
+                                        use_atomics, h->d_prec.p + recoff, h->nfct);
   }
   else
   {
@@ -1066,10 +1068,11 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
   h->launches++;
 }
 
-void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf)
+void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf, int lanes,
+               int64_t recoff)
 {
   if (ev)
-    launch_k2_range<true>(h, ptrs, first, count, use_atomics, maxnf);
+    launch_k2_range<true>(h, ptrs, first, count, use_atomics, maxnf, lanes, recoff);
   else
-    launch_k2_range<false>(h, ptrs, first, count, use_atomics, maxnf);
+    launch_k2_range<false>(h, ptrs, first, count, use_atomics, maxnf, lanes, recoff);
 }

@@ -98,7 +98,7 @@ template <int K, bool EV, int S>
 __global__ void __launch_bounds__(128, (K == 2 ? 4 : 2))
 patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ tab, const double* __restrict__ cellJ, int nrhs,
                 RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
-                const int32_t* __restrict__ cell_fct, int nfct)
+                const int4* __restrict__ rec, int nfct)
 {
   using D = KW<K>;
   constexpr int B = D::B, nadd = D::nadd, ndiv = D::ndiv, NT = D::NT, NDG = D::NDG, nrt = D::nrt, nact = D::nact,
@@ -120,10 +120,12 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
   const int p = warp * PPW + lane / S;
   const bool valid = p < count;
   const size_t ip = (size_t)first + (valid ? p : 0);
-  const int nc = valid ? pv.ncells[ip] : 0;
+  // one coalesced 16-byte record per lane (segments are padded with zero records)
+  const int4 rc = rec[(size_t)warp * 32 + lane];
+  const int nc = valid ? (rc.y >> 16) : 0;
   const bool active = j < nc;
-  const int32_t c = active ? pv.cell[(size_t)j * pv.stride + ip] : 0;
-  const int info = active ? pv.info[(size_t)j * pv.stride + ip] : 0;
+  const int32_t c = rc.x;
+  const int info = active ? (rc.y & 0xffff) : 0;
   const int v = info & 3, fm = (info >> 2) & 3, fp = active ? (info >> 4) & 3 : 1;
   const bool rev0 = (info & 64) != 0, rev1 = (info & 128) != 0;
   const bool first_c = (j == 0), last_c = (j == nc - 1);
@@ -902,9 +904,8 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
       {
         for (int side = (first_c && !internal) ? 0 : 1; side < 2; ++side)
         {
-          const int fl = side ? fp : fm;
           const bool refl = (info & (side ? 512 : 256)) != 0;
-          double* d = sig + (size_t)cell_fct[3 * (size_t)c + fl] * K;
+          double* d = sig + (size_t)(side ? rc.w : rc.z) * K;
 #pragma unroll
           for (int i = 0; i < K; ++i)
           {
@@ -1013,18 +1014,19 @@ void build_kw_tables_t(eqlb_handle* h, const eqlb_tables* t, DevBuf<double>& dst
 }
 
 template <int K, bool EV>
-void launch_kw_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf)
+void launch_kw_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int S, int64_t recoff)
 {
   using D = KW<K>;
   const int bs = 128;
   const size_t smem = (size_t)D::TAB * sizeof(double);
-  const int S = maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16);
+  if ((S != 4 && S != 8 && S != 16) || recoff < 0)
+    throw EqlbError(EQLB_ERR_STATE, "warp-cooperative kernel: segment without lane records");
   const int ppb = bs / S;
   const int grid = (count + ppb - 1) / ppb;
   auto kern = (S == 4) ? patch_kw_kernel<K, EV, 4> : (S == 8 ? patch_kw_kernel<K, EV, 8> : patch_kw_kernel<K, EV, 16>);
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, bs, smem, h->stream>>>(h->patch_view(), first, count, h->d_kwtab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p,
-                                      (size_t)h->ncell * h->nrt, use_atomics, h->d_cell_fct.p, h->nfct);
+                                      (size_t)h->ncell * h->nrt, use_atomics, h->d_prec.p + recoff, h->nfct);
   CUDA_CHECK(cudaGetLastError());
   h->launches++;
 }
@@ -1041,22 +1043,22 @@ void build_kw_tables(eqlb_handle* h, const eqlb_tables* t)
     build_kw_tables_t<3>(h, t, h->d_kwtab);
 }
 
-void launch_kw(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf)
+void launch_kw(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff)
 {
   if (count <= 0)
     return;
   if (h->k == 2)
   {
     if (ev)
-      launch_kw_t<2, true>(h, ptrs, first, count, use_atomics, maxnf);
+      launch_kw_t<2, true>(h, ptrs, first, count, use_atomics, lanes, recoff);
     else
-      launch_kw_t<2, false>(h, ptrs, first, count, use_atomics, maxnf);
+      launch_kw_t<2, false>(h, ptrs, first, count, use_atomics, lanes, recoff);
   }
   else
   {
     if (ev)
-      launch_kw_t<3, true>(h, ptrs, first, count, use_atomics, maxnf);
+      launch_kw_t<3, true>(h, ptrs, first, count, use_atomics, lanes, recoff);
     else
-      launch_kw_t<3, false>(h, ptrs, first, count, use_atomics, maxnf);
+      launch_kw_t<3, false>(h, ptrs, first, count, use_atomics, lanes, recoff);
   }
 }

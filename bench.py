@@ -210,10 +210,10 @@ def main():
         bcs = [[] for _ in range(nrhs)]
         npatch_total = nnode_global
     if args.path == "se":
-        eq = eqlb.FluxEqlbSE(k, m, F, G, node_owned=node_owned)
+        eq = eqlb.FluxEqlbSE(k, m, F, G, node_owned=node_owned, host_pipeline=False)
         nout = m.ncell * T.nrt
     else:
-        eq = eqlb.FluxEqlbEV(k, m, F, G, node_owned=node_owned)
+        eq = eqlb.FluxEqlbEV(k, m, F, G, node_owned=node_owned, host_pipeline=False)
         nout = eq.ndofs
     eq.set_boundary_conditions(bfct, bcs)
     prob = eq.problem
@@ -283,6 +283,14 @@ def main():
     hF = [torch.from_numpy(f).pin_memory() for f in F]
     hS = [torch.zeros(nout, dtype=torch.float64).pin_memory() for _ in range(nrhs)]
     qG, qF, qS = dptrs(hG), dptrs(hF), dptrs(hS)
+    hprob = prob
+    if world == 1:
+        # the user-facing default for host arrays: staged copy-in / kernels / copy-out
+        cls = eqlb.FluxEqlbSE if args.path == "se" else eqlb.FluxEqlbEV
+        heq = cls(k, m, F, G, host_pipeline=True)
+        heq.set_boundary_conditions(bfct, bcs)
+        hprob = heq.problem
+        hprob.set_stream(stream.cuda_stream)
 
     def step_host():
         if world > 1:
@@ -293,10 +301,11 @@ def main():
                 h_.copy_(d, non_blocking=True)
             torch.cuda.synchronize()
             return
+        # EQLB_HOST_ZEROED: the flux starts from zero as in the reference's equilibrate_fluxes
         if args.path == "se":
-            rc = lib.eqlb_se_run(prob.h, qG, qF, qS, cabi.c_double_p(), 0)
+            rc = lib.eqlb_se_run(hprob.h, qG, qF, qS, cabi.c_double_p(), 2)
         else:
-            rc = lib.eqlb_ev_run(prob.h, qG, qF, qS, 0)
+            rc = lib.eqlb_ev_run(hprob.h, qG, qF, qS, 2)
         if rc != 0:
             raise RuntimeError(lib.eqlb_last_error().decode())
 
@@ -312,7 +321,9 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF) + sum(s.numel() * 8 for s in hS)
+    h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF)
+    if world > 1:
+        h2d += sum(s.numel() * 8 for s in hS)
     d2h = sum(s.numel() * 8 for s in hS)
 
     if dist is not None:

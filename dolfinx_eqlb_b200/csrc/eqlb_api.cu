@@ -84,9 +84,26 @@ void colour_patches(eqlb_handle* h)
   long chunk_cells = 1L << 40;  // default: one chunk (measured on B200: chunking only adds launch tails, the kernel is not DRAM bound)
   if (const char* e = getenv("EQLB_CHUNK_CELLS"))
     chunk_cells = std::max(1L, atol(e));
-  const int nchunk = (int)std::max<long>(1, ((long)h->ncell + chunk_cells - 1) / chunk_cells);
+  int nchunk = (int)std::max<long>(1, ((long)h->ncell + chunk_cells - 1) / chunk_cells);
+  if (h->flags & EQLB_FLAG_HOST_PIPELINE)
+  {
+    // host pipeline: about 128k cells per stage, 4..16 stages
+    nchunk = (int)std::min<long>(16, std::max<long>(4, h->ncell / 262144));
+    if (const char* e = getenv("EQLB_PIPE_STAGES"))
+      nchunk = std::max(1, atoi(e));
+    if (h->ncell < 4096)
+      nchunk = 1;
+  }
+  h->nchunk = nchunk;
+  // stage of a patch = chunk of its LAST cell: all its inputs are on the device once the
+  // cell slabs 0..stage have arrived
   auto chunk_of = [&](int z)
-  { return (int)((long)h->h_node_cell[h->h_node_cell_off[z]] * nchunk / std::max(h->ncell, 1)); };
+  {
+    int32_t cmax = 0;
+    for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
+      cmax = std::max(cmax, h->h_node_cell[i]);
+    return (int)((long)cmax * nchunk / std::max(h->ncell, 1));
+  };
   h->nseg = nchunk * ncol;
   h->h_colour_off.assign(h->nseg + 1, 0);
   auto seg_of = [&](int z) { return chunk_of(z) * ncol + h->h_colour[z]; };
@@ -119,6 +136,37 @@ void colour_patches(eqlb_handle* h)
           h->h_colour_maxnf[sg] = std::max(h->h_colour_maxnf[sg], h->h_node_fct_off[z + 1] - h->h_node_fct_off[z]);
         }
       }
+
+  // result ranges of the host pipeline: a range of DOFs can go back to the host after the
+  // last stage with a patch that adds into it
+  h->h_se_slabs.clear();
+  h->h_ev_slabs.clear();
+  if (nchunk > 1)
+  {
+    std::vector<int> nstage(n, -1);
+    for (int z = 0; z < n; ++z)
+      if (h->h_owned[z] && !h->h_grouped[z])
+        nstage[z] = chunk_of(z);
+    auto slab_lo = [&](long cnt, int sidx) { return (size_t)(cnt * sidx / nchunk); };
+    const int kk = h->k;
+    const size_t ncd = (size_t)(kk * kk - kk);
+    for (int sidx = 0; sidx < nchunk; ++sidx)
+    {
+      const size_t c0 = slab_lo(h->ncell, sidx), c1 = slab_lo(h->ncell, sidx + 1);
+      int fin = 0;
+      for (size_t c = c0; c < c1; ++c)
+        for (int j = 0; j < 3; ++j)
+          fin = std::max(fin, nstage[h->h_cell_node[3 * c + j]]);
+      h->h_se_slabs.push_back({c0 * h->nrt, (c1 - c0) * h->nrt, fin});
+      if (ncd)
+        h->h_ev_slabs.push_back({(size_t)h->nfct * kk + c0 * ncd, (c1 - c0) * ncd, fin});
+      const size_t f0 = slab_lo(h->nfct, sidx), f1 = slab_lo(h->nfct, sidx + 1);
+      int ffin = 0;
+      for (size_t f = f0; f < f1; ++f)
+        ffin = std::max(ffin, std::max(nstage[h->h_fct_node[2 * f]], nstage[h->h_fct_node[2 * f + 1]]));
+      h->h_ev_slabs.push_back({f0 * kk, (f1 - f0) * kk, ffin});
+    }
+  }
 }
 
 void append(std::vector<double>& dst, const double* src, size_t n, int& offset)
@@ -130,6 +178,20 @@ void append(std::vector<double>& dst, const double* src, size_t n, int& offset)
 }
 
 } // namespace
+
+eqlb_handle::~eqlb_handle()
+{
+  for (cudaEvent_t e : ev_in)
+    cudaEventDestroy(e);
+  for (cudaEvent_t e : ev_done)
+    cudaEventDestroy(e);
+  if (ev_start)
+    cudaEventDestroy(ev_start);
+  if (s_h2d)
+    cudaStreamDestroy(s_h2d);
+  if (s_d2h)
+    cudaStreamDestroy(s_d2h);
+}
 
 extern "C"
 {
@@ -316,6 +378,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
 }
 
 void eqlb_destroy(eqlb_handle* h) { delete h; }
+
 
 int eqlb_set_stream(eqlb_handle* h, void* cuda_stream)
 {
@@ -558,112 +621,159 @@ int eqlb_get_se_dofmaps(eqlb_handle* h, int32_t* dofmap, int32_t* projflux_fct, 
       });
 }
 
+// Common driver of eqlb_se_run / eqlb_ev_run: device pointers are used in place; host
+// pointers are staged, either in one piece or - with EQLB_FLAG_HOST_PIPELINE - stage by
+// stage on three streams so that both PCIe directions and the SMs work at the same time.
+static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, const double* const* f,
+                              double* const* sigma, double* korn, int memspace)
+{
+  const char* who = ev ? "eqlb_ev_run" : "eqlb_se_run";
+  if (!h || !G || !f || !sigma)
+    throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": null argument");
+  if (!h->bcs_set)
+    throw EqlbError(EQLB_ERR_STATE, std::string(who) + ": call eqlb_set_bcs first");
+  if (memspace != EQLB_HOST && memspace != EQLB_DEVICE && memspace != EQLB_HOST_ZEROED)
+    throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": unknown memspace");
+  const int nrhs = h->nrhs;
+  const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg;
+  const size_t nS = ev ? (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k) : (size_t)h->ncell * h->nrt;
+  const double* dG[EQLB_MAXRHS];
+  const double* dF[EQLB_MAXRHS];
+  double* dS[EQLB_MAXRHS];
+  double* dK = korn;
+  auto launch = [&]
+  {
+    if (ev)
+      launch_ev(h, dG, dF, dS);
+    else
+      launch_se(h, dG, dF, dS, dK);
+  };
+  if (memspace == EQLB_DEVICE)
+  {
+    for (int r = 0; r < nrhs; ++r)
+    {
+      dG[r] = G[r];
+      dF[r] = f[r];
+      dS[r] = sigma[r];
+    }
+    launch();
+    return;
+  }
+  const bool zeroed = (memspace == EQLB_HOST_ZEROED);
+  h->d_stage_G.alloc(nG * nrhs);
+  h->d_stage_f.alloc(nF * nrhs);
+  h->d_stage_sigma.alloc(nS * nrhs);
+  for (int r = 0; r < nrhs; ++r)
+  {
+    dG[r] = h->d_stage_G.p + r * nG;
+    dF[r] = h->d_stage_f.p + r * nF;
+    dS[r] = h->d_stage_sigma.p + r * nS;
+  }
+  if (korn)
+  {
+    h->d_stage_korn.alloc(h->ncell);
+    dK = h->d_stage_korn.p;
+  }
+  const bool pipelined = h->nchunk > 1 && !(h->flags & (EQLB_FLAG_STRESS | EQLB_FLAG_ATOMIC)) && h->h_group_off.empty()
+                         && !korn && h->nseg == h->nchunk * h->ncolours;
+  if (!pipelined)
+  {
+    for (int r = 0; r < nrhs; ++r)
+    {
+      CUDA_CHECK(cudaMemcpyAsync((void*)dG[r], G[r], nG * 8, cudaMemcpyHostToDevice, h->stream));
+      CUDA_CHECK(cudaMemcpyAsync((void*)dF[r], f[r], nF * 8, cudaMemcpyHostToDevice, h->stream));
+      if (zeroed)
+        CUDA_CHECK(cudaMemsetAsync(dS[r], 0, nS * 8, h->stream));
+      else
+        CUDA_CHECK(cudaMemcpyAsync(dS[r], sigma[r], nS * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (korn)
+      CUDA_CHECK(cudaMemcpyAsync(dK, korn, (size_t)h->ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    launch();
+    for (int r = 0; r < nrhs; ++r)
+      CUDA_CHECK(cudaMemcpyAsync(sigma[r], dS[r], nS * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (korn)
+      CUDA_CHECK(cudaMemcpyAsync(korn, dK, (size_t)h->ncell * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return;
+  }
+
+  // ---- staged: copy-in stream, compute stream (the caller's), copy-out stream ----
+  const int nst = h->nchunk;
+  if (!h->s_h2d)
+  {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  }
+  while ((int)h->ev_in.size() < nst)
+  {
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_in.push_back(a);
+    h->ev_done.push_back(b);
+  }
+  // everything queued on the caller's stream so far happens before the first copy
+  CUDA_CHECK(cudaEventRecord(h->ev_start, h->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_start, 0));
+  for (int r = 0; r < nrhs; ++r)
+  {
+    if (zeroed)
+      CUDA_CHECK(cudaMemsetAsync(dS[r], 0, nS * 8, h->stream));
+    else
+      CUDA_CHECK(cudaMemcpyAsync(dS[r], sigma[r], nS * 8, cudaMemcpyHostToDevice, h->s_h2d));
+  }
+  auto cell_lo = [&](int sidx) { return (size_t)((long)h->ncell * sidx / nst); };
+  for (int sidx = 0; sidx < nst; ++sidx)
+  {
+    const size_t c0 = cell_lo(sidx), nc = cell_lo(sidx + 1) - c0;
+    for (int r = 0; r < nrhs && nc; ++r)
+    {
+      const size_t og = c0 * h->ndg * 2, of = c0 * h->ndg;
+      CUDA_CHECK(cudaMemcpyAsync((void*)(dG[r] + og), G[r] + og, nc * h->ndg * 16, cudaMemcpyHostToDevice, h->s_h2d));
+      CUDA_CHECK(cudaMemcpyAsync((void*)(dF[r] + of), f[r] + of, nc * h->ndg * 8, cudaMemcpyHostToDevice, h->s_h2d));
+    }
+    CUDA_CHECK(cudaEventRecord(h->ev_in[sidx], h->s_h2d));
+  }
+  const auto& slabs = ev ? h->h_ev_slabs : h->h_se_slabs;
+  try
+  {
+    for (int sidx = 0; sidx < nst; ++sidx)
+    {
+      CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in[sidx], 0));
+      h->win_lo = sidx * h->ncolours;
+      h->win_hi = (sidx + 1) * h->ncolours;
+      launch();
+      CUDA_CHECK(cudaEventRecord(h->ev_done[sidx], h->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[sidx], 0));
+      for (const auto& sl : slabs)
+        if (sl.final_stage == sidx && sl.len)
+          for (int r = 0; r < nrhs; ++r)
+            CUDA_CHECK(cudaMemcpyAsync(sigma[r] + sl.off, dS[r] + sl.off, sl.len * 8, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+  }
+  catch (...)
+  {
+    h->win_lo = 0;
+    h->win_hi = 1 << 30;
+    throw;
+  }
+  h->win_lo = 0;
+  h->win_hi = 1 << 30;
+  CUDA_CHECK(cudaStreamSynchronize(h->s_d2h));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
 int eqlb_se_run(eqlb_handle* h, const double* const* G, const double* const* f, double* const* sigma, double* korn,
                 int memspace)
 {
-  return guarded(
-      [&]
-      {
-        if (!h || !G || !f || !sigma)
-          throw EqlbError(EQLB_ERR_INPUT, "eqlb_se_run: null argument");
-        if (!h->bcs_set)
-          throw EqlbError(EQLB_ERR_STATE, "eqlb_se_run: call eqlb_set_bcs first");
-        const int nrhs = h->nrhs;
-        const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg,
-                     nS = (size_t)h->ncell * h->nrt;
-        const double* dG[EQLB_MAXRHS];
-        const double* dF[EQLB_MAXRHS];
-        double* dS[EQLB_MAXRHS];
-        double* dK = korn;
-        if (memspace == EQLB_DEVICE)
-        {
-          for (int r = 0; r < nrhs; ++r)
-          {
-            dG[r] = G[r];
-            dF[r] = f[r];
-            dS[r] = sigma[r];
-          }
-        }
-        else
-        {
-          h->d_stage_G.alloc(nG * nrhs);
-          h->d_stage_f.alloc(nF * nrhs);
-          h->d_stage_sigma.alloc(nS * nrhs);
-          for (int r = 0; r < nrhs; ++r)
-          {
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_G.p + r * nG, G[r], nG * 8, cudaMemcpyHostToDevice, h->stream));
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_f.p + r * nF, f[r], nF * 8, cudaMemcpyHostToDevice, h->stream));
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_sigma.p + r * nS, sigma[r], nS * 8, cudaMemcpyHostToDevice, h->stream));
-            dG[r] = h->d_stage_G.p + r * nG;
-            dF[r] = h->d_stage_f.p + r * nF;
-            dS[r] = h->d_stage_sigma.p + r * nS;
-          }
-          if (korn)
-          {
-            h->d_stage_korn.alloc(h->ncell);
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_korn.p, korn, (size_t)h->ncell * 8, cudaMemcpyHostToDevice, h->stream));
-            dK = h->d_stage_korn.p;
-          }
-        }
-        launch_se(h, dG, dF, dS, dK);
-        if (memspace != EQLB_DEVICE)
-        {
-          for (int r = 0; r < nrhs; ++r)
-            CUDA_CHECK(cudaMemcpyAsync(sigma[r], dS[r], nS * 8, cudaMemcpyDeviceToHost, h->stream));
-          if (korn)
-            CUDA_CHECK(cudaMemcpyAsync(korn, dK, (size_t)h->ncell * 8, cudaMemcpyDeviceToHost, h->stream));
-          CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        }
-      });
+  return guarded([&] { run_equilibration(h, false, G, f, sigma, korn, memspace); });
 }
 
 int eqlb_ev_run(eqlb_handle* h, const double* const* G, const double* const* f, double* const* sigma, int memspace)
 {
-  return guarded(
-      [&]
-      {
-        if (!h || !G || !f || !sigma)
-          throw EqlbError(EQLB_ERR_INPUT, "eqlb_ev_run: null argument");
-        if (!h->bcs_set)
-          throw EqlbError(EQLB_ERR_STATE, "eqlb_ev_run: call eqlb_set_bcs first");
-        const int nrhs = h->nrhs;
-        const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg,
-                     nS = (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k);
-        const double* dG[EQLB_MAXRHS];
-        const double* dF[EQLB_MAXRHS];
-        double* dS[EQLB_MAXRHS];
-        if (memspace == EQLB_DEVICE)
-        {
-          for (int r = 0; r < nrhs; ++r)
-          {
-            dG[r] = G[r];
-            dF[r] = f[r];
-            dS[r] = sigma[r];
-          }
-        }
-        else
-        {
-          h->d_stage_G.alloc(nG * nrhs);
-          h->d_stage_f.alloc(nF * nrhs);
-          h->d_stage_sigma.alloc(nS * nrhs);
-          for (int r = 0; r < nrhs; ++r)
-          {
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_G.p + r * nG, G[r], nG * 8, cudaMemcpyHostToDevice, h->stream));
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_f.p + r * nF, f[r], nF * 8, cudaMemcpyHostToDevice, h->stream));
-            CUDA_CHECK(cudaMemcpyAsync(h->d_stage_sigma.p + r * nS, sigma[r], nS * 8, cudaMemcpyHostToDevice, h->stream));
-            dG[r] = h->d_stage_G.p + r * nG;
-            dF[r] = h->d_stage_f.p + r * nF;
-            dS[r] = h->d_stage_sigma.p + r * nS;
-          }
-        }
-        launch_ev(h, dG, dF, dS);
-        if (memspace != EQLB_DEVICE)
-        {
-          for (int r = 0; r < nrhs; ++r)
-            CUDA_CHECK(cudaMemcpyAsync(sigma[r], dS[r], nS * 8, cudaMemcpyDeviceToHost, h->stream));
-          CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        }
-      });
+  return guarded([&] { run_equilibration(h, true, G, f, sigma, nullptr, memspace); });
 }
 
 int eqlb_local_project(eqlb_handle* h, int nfun, const double* const* qvals, double* const* out, int memspace)

@@ -202,6 +202,20 @@ struct eqlb_handle
   std::vector<int32_t> h_seg_lanes;     // [nseg] lanes per patch (4, 8, 16; 0: none)
   DevBuf<int64_t> d_seginfo;            // [nseg][4] first, nfast, lanes, recoff
 
+  // host pipeline (EQLB_FLAG_HOST_PIPELINE): spatial stages = chunks of the cell range
+  int nchunk = 1;
+  int win_lo = 0, win_hi = 1 << 30;  // window of launch segments executed by launch_se / launch_ev
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
+  cudaEvent_t ev_start = nullptr;
+  struct OutSlab
+  {
+    size_t off, len;  // range of the per-RHS result vector (doubles)
+    int final_stage;  // last stage that adds into the range
+  };
+  std::vector<OutSlab> h_se_slabs, h_ev_slabs;
+  ~eqlb_handle();
+
   // staging buffers for host-pointer calls
   DevBuf<double> d_stage_G, d_stage_f, d_stage_sigma, d_stage_korn;
 

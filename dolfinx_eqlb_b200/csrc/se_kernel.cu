@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "eqlb_internal.cuh"
 
 namespace
@@ -1317,7 +1319,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   }
   else
   {
-    for (int c = 0; c < h->nseg; ++c)
+    for (int c = std::max(0, h->win_lo); c < std::min(h->nseg, h->win_hi); ++c)
     {
       int first = h->h_colour_off[c];
       int count = h->h_colour_off[c + 1] - first;

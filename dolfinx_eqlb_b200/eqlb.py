@@ -100,12 +100,13 @@ def boundarydata(list_bcs, mesh, tables, list_bfcts_prime, equilibrate_stress=Fa
 class _Problem:
     """Owns the device-resident problem (C-ABI handle)."""
 
-    def __init__(self, mesh: Mesh, tables: Tables, nrhs: int, stress=False, atomic=False, node_owned=None):
+    def __init__(self, mesh: Mesh, tables: Tables, nrhs: int, stress=False, atomic=False, node_owned=None,
+                 host_pipeline=False):
         self.lib = cabi.load_library()
         self.mesh, self.tables, self.nrhs = mesh, tables, nrhs
         self._pm = cabi.PackedMesh(mesh, tables.ndg, node_owned)
         self._pt = cabi.PackedTables(tables)
-        flags = (1 if stress else 0) | (2 if atomic else 0)
+        flags = (1 if stress else 0) | (2 if atomic else 0) | (16 if host_pipeline else 0)
         self.stress = stress
         h = C.c_void_p()
         _check(self.lib, self.lib.eqlb_create(C.byref(self._pm.struct), C.byref(self._pt.struct), nrhs, flags, C.byref(h)))
@@ -193,9 +194,10 @@ def _as_ptr_list(arrs):
     return [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
 
 
-def reconstruct_fluxes_semiexplt(problem: _Problem, flux_hdiv, flux_dg, rhs_dg, korn=None):
+def reconstruct_fluxes_semiexplt(problem: _Problem, flux_hdiv, flux_dg, rhs_dg, korn=None, zeroed=False):
     """`cpp.reconstruct_fluxes_semiexplt[_with_kornconst]` (`wrappers.cpp:97-137`):
-    host numpy vectors, accumulated in place into `flux_hdiv`."""
+    host numpy vectors, accumulated in place into `flux_hdiv` (`zeroed`: the caller
+    guarantees `flux_hdiv` is zero on entry, its upload is skipped)."""
     lib = problem.lib
     G, F = _as_ptr_list(flux_dg), _as_ptr_list(rhs_dg)
     for s in flux_hdiv:
@@ -204,17 +206,17 @@ def reconstruct_fluxes_semiexplt(problem: _Problem, flux_hdiv, flux_dg, rhs_dg, 
     if not (len(G) == len(F) == len(flux_hdiv) == problem.nrhs):
         raise RuntimeError("Equilibration: Input sizes does not match")
     kp = korn.ctypes.data_as(cabi.c_double_p) if korn is not None else cabi.c_double_p()
-    _check(lib, lib.eqlb_se_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), kp, 0))
+    _check(lib, lib.eqlb_se_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), kp, 2 if zeroed else 0))
 
 
-def reconstruct_fluxes_minimisation(problem: _Problem, flux_hdiv, flux_dg, rhs_dg):
+def reconstruct_fluxes_minimisation(problem: _Problem, flux_hdiv, flux_dg, rhs_dg, zeroed=False):
     """`cpp.reconstruct_fluxes_minimisation` (`wrappers.cpp:85-95`) for the fixed
     forms of `FluxEqlbEV.py:116-133`."""
     lib = problem.lib
     G, F = _as_ptr_list(flux_dg), _as_ptr_list(rhs_dg)
     if not (len(G) == len(F) == len(flux_hdiv) == problem.nrhs):
         raise RuntimeError("Equilibration: Input sizes does not match")
-    _check(lib, lib.eqlb_ev_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), 0))
+    _check(lib, lib.eqlb_ev_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), 2 if zeroed else 0))
 
 
 class FluxEquilibrator:
@@ -233,7 +235,7 @@ class FluxEqlbSE(FluxEquilibrator):
     """`eqlb/FluxEqlbSE.py:24-198` on top of the CUDA hot path."""
 
     def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, equilibrate_stress=False,
-                 estimate_korn_constant=False, degree_proj=None, atomic=False, node_owned=None):
+                 estimate_korn_constant=False, degree_proj=None, atomic=False, node_owned=None, host_pipeline=True):
         super().__init__(degree_flux, len(list_rhs), equilibrate_stress)
         if len(list_proj_flux) != self.n_fluxes:
             raise RuntimeError("Mismatching inputs!")
@@ -242,8 +244,9 @@ class FluxEqlbSE(FluxEquilibrator):
         self.list_rhs, self.list_proj_flux = list_rhs, list_proj_flux
         self.estimate_korn_constant = estimate_korn_constant
         self.korn_constants = np.zeros(msh.ncell) if estimate_korn_constant else None
-        self.problem = _Problem(msh, self.tables, self.n_fluxes, equilibrate_stress, atomic, node_owned)
+        self.problem = _Problem(msh, self.tables, self.n_fluxes, equilibrate_stress, atomic, node_owned, host_pipeline)
         self.list_flux = [np.zeros(msh.ncell * self.tables.nrt) for _ in range(self.n_fluxes)]
+        self._fresh = True  # list_flux still holds the zeros it was created with
 
     def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
@@ -253,7 +256,9 @@ class FluxEqlbSE(FluxEquilibrator):
         self.problem.set_bcs(self.boundary_data)
 
     def equilibrate_fluxes(self):
-        reconstruct_fluxes_semiexplt(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, self.korn_constants)
+        reconstruct_fluxes_semiexplt(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, self.korn_constants,
+                                     zeroed=self._fresh)
+        self._fresh = False
         if self.estimate_korn_constant:
             self.korn_constants[:] = np.sqrt(self.korn_constants)
 
@@ -267,17 +272,18 @@ class FluxEqlbEV(FluxEquilibrator):
     """`eqlb/FluxEqlbEV.py:20-188` on top of the CUDA hot path; the flux lives in
     the conforming hierarchic RT_k space ([facet dofs nfct*k][cell dofs])."""
 
-    def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, node_owned=None):
+    def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, node_owned=None, host_pipeline=True):
         super().__init__(degree_flux, len(list_rhs), False)
         if len(list_proj_flux) != self.n_fluxes:
             raise RuntimeError("Missmatching inputs!")
         self.mesh = msh
         self.tables = make_tables(degree_flux)
         self.list_rhs, self.list_proj_flux = list_rhs, list_proj_flux
-        self.problem = _Problem(msh, self.tables, self.n_fluxes, False, False, node_owned)
+        self.problem = _Problem(msh, self.tables, self.n_fluxes, False, False, node_owned, host_pipeline)
         k = degree_flux
         self.ndofs = msh.nfct * k + msh.ncell * (k * k - k)
         self.list_flux = [np.zeros(self.ndofs) for _ in range(self.n_fluxes)]
+        self._fresh = True
 
     def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
@@ -287,7 +293,8 @@ class FluxEqlbEV(FluxEquilibrator):
         self.problem.set_bcs(self.boundary_data)
 
     def equilibrate_fluxes(self):
-        reconstruct_fluxes_minimisation(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs)
+        reconstruct_fluxes_minimisation(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, zeroed=self._fresh)
+        self._fresh = False
 
 
 def local_projection(problem: _Problem, qvals):

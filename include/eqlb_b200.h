@@ -31,6 +31,10 @@ extern "C" {
 
 #define EQLB_HOST 0
 #define EQLB_DEVICE 1
+/* host pointers; sigma is taken as zero on entry and not read (what the reference does in
+ * practice: `FluxEqlbSE.py:79-81` creates zero flux functions and equilibrates into them
+ * once), which saves the host->device copy of sigma */
+#define EQLB_HOST_ZEROED 2
 
 #define EQLB_OK 0
 #define EQLB_ERR_INPUT (-1)   /* the reference's std::runtime_error on bad input */
@@ -42,6 +46,10 @@ extern "C" {
 #define EQLB_FLAG_ATOMIC 2u   /* accumulate with fp64 atomics instead of colour-ordered launches */
 #define EQLB_FLAG_GENERIC 4u  /* always use the generic patch kernel (no degree-2 streaming kernel) */
 #define EQLB_FLAG_K2_THREAD 8u /* degree 2: thread-per-patch streaming kernel instead of lane-per-cell */
+/* host-pointer calls stream the mesh through the GPU in spatial stages: host->device copy of
+ * stage s+1, patch kernels of stage s and device->host copy of finished DOF ranges overlap on
+ * three streams (PCIe both directions busy); costs a few extra launches on device-pointer calls */
+#define EQLB_FLAG_HOST_PIPELINE 16u
 
 /* wire values, `base/Patch.hpp:20-33` */
 enum eqlb_patch_type { EQLB_PATCH_INTERNAL = 0, EQLB_PATCH_ESSNT_DUAL = 1,

@@ -1,0 +1,61 @@
+"""Host-pointer calls staged through the GPU (EQLB_FLAG_HOST_PIPELINE): copy-in, patch
+kernels and copy-out of spatial stages overlap on three streams.  The staged result must
+agree with the one-piece result (same patches, other summation order per DOF) and with
+the oracle."""
+
+import numpy as np
+import pytest
+
+from common import PoissonCase, make_mesh
+from dolfinx_eqlb_b200 import eqlb
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def run(case, path, pipeline, twice=False):
+    cls = eqlb.FluxEqlbSE if path == "se" else eqlb.FluxEqlbEV
+    eq = cls(case.k, case.mesh, case.F, case.G, host_pipeline=pipeline)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    eq.equilibrate_fluxes()  # zero flux on entry: EQLB_HOST_ZEROED
+    if twice:
+        eq.equilibrate_fluxes()  # accumulates: EQLB_HOST
+    return eq
+
+
+@pytest.mark.parametrize("path", ["se", "ev"])
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("scramble", [None, 5])
+def test_staged_equals_one_piece(monkeypatch, path, k, scramble):
+    monkeypatch.setenv("EQLB_PIPE_STAGES", "5")
+    m = make_mesh("crossed", 36, scramble, perturb=0.2)  # 5184 cells: above the staging threshold
+    case = PoissonCase(m, k, [[1, 4], [2]], seed=3, hom=False)
+    a = run(case, path, False)
+    b = run(case, path, True)
+    _, _, ncol = b.problem.patch_dims()
+    for r in range(case.nrhs):
+        assert rel_err(b.list_flux[r], a.list_flux[r]) < 1e-12
+
+
+@pytest.mark.parametrize("path", ["se", "ev"])
+def test_staged_accumulates(monkeypatch, path):
+    monkeypatch.setenv("EQLB_PIPE_STAGES", "4")
+    m = make_mesh("crossed", 34, None, perturb=0.2)
+    case = PoissonCase(m, 2, [[1, 3]], seed=5, hom=False)
+    once = run(case, path, True)
+    twice = run(case, path, True, twice=True)
+    assert rel_err(twice.list_flux[0], 2.0 * once.list_flux[0]) < 1e-12
+
+
+def test_staged_oracle_parity(monkeypatch):
+    from oracle import pyoracle as po
+
+    monkeypatch.setenv("EQLB_PIPE_STAGES", "7")
+    m = make_mesh("crossed", 33, None, perturb=0.2)
+    case = PoissonCase(m, 2, [[1, 4]], seed=9, hom=False)
+    ref = po.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    eq = run(case, "ev", True)
+    assert rel_err(eq.list_flux[0], ref[0]) < 1e-10

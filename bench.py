@@ -98,51 +98,74 @@ def build_case(n, k, nrhs):
     return m, T, G, F, bfct, bcs
 
 
-def time_oracle(path, n, k, nrhs, repeats):
-    """CPU baseline: the oracle restatement (reference loop structure, 1 thread) on a
-    bounded sample of the same workload; min over repeats like perftest.py:39-40."""
+def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue):
+    """One host process = one rank of the reference's MPI-parallel CPU path: it equilibrates
+    its own n x n block (no communication: an upper bound of the reference's scaling)."""
     from oracle import pyoracle as po
     from dolfinx_eqlb_b200 import mesh as ms
 
     m, T, G, F, bfct, bcs = build_case(n, k, nrhs)
     ft = np.stack([ms.facet_types(m, [1, 2, 3, 4], []) for _ in range(nrhs)])
     bc = po.BCData(ft)
-    best = None
-    for _ in range(repeats):
+    run = (lambda: po.se_run(m, T, bc, G, F)) if path == "se" else (lambda: po.ev_run(m, T, bc, G, F))
+    for _ in range(warmup):
+        run()
+    barrier.wait()
+    dts = []
+    for _ in range(steps):
         t0 = time.perf_counter()
-        if path == "se":
-            po.se_run(m, T, bc, G, F)
-        else:
-            po.ev_run(m, T, bc, G, F)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return m.nnode / best, m.nnode, best
+        run()
+        dts.append(time.perf_counter() - t0)
+    queue.put((m.nnode, dts))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None):
+    """CPU baseline: the oracle restatement (reference loop structure) on a bounded sample
+    of the same workload, one process per host core like the reference under mpirun.
+    Returns (patches/s over all processes, patches per process, seconds per step, processes)."""
+    import multiprocessing as mp
+
+    procs = procs or min(host_cores(), 128)
+    ctx = mp.get_context("spawn")
+    barrier, queue = ctx.Barrier(procs), ctx.Queue()
+    ws = [ctx.Process(target=_oracle_worker, args=(path, n, k, nrhs, warmup, steps, barrier, queue)) for _ in range(procs)]
+    for w in ws:
+        w.start()
+    res = [queue.get() for _ in ws]
+    for w in ws:
+        w.join()
+    npatch = res[0][0]
+    # a step ends when the slowest process has finished it
+    step_s = [max(r[1][i] for r in res) for i in range(steps)]
+    sec = float(np.mean(step_s))
+    return procs * npatch / sec, npatch, sec, procs
 
 
 def reference_arm(args):
     """`--impl reference`: the reference's CPU algorithm (oracle port; the reference
-    itself cannot be built here - SURVEY 8c) on the box's host cores."""
+    itself cannot be built here - SURVEY 8c) on all host cores of the box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_sample = args.cpu_n
-    vals = []
-    for _ in range(max(args.warmup, 0)):
-        time_oracle(args.path, n_sample, args.k, args.nrhs, 1)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v, npatch, dt = time_oracle(args.path, n_sample, args.k, args.nrhs, 1)
-        vals.append((v, dt))
+    value, npatch, sec, procs = time_oracle(args.path, n_sample, args.k, args.nrhs, args.steps, max(args.warmup, 0))
     total = time.perf_counter() - t0
-    value = float(np.mean([v for v, _ in vals]))
-    ms_step = 1e3 * float(np.mean([d for _, d in vals]))
-    sample = f"crossed {n_sample}x{n_sample} ({npatch} patches) of the {args.n}x{args.n} workload, 1 thread, mean of {args.steps} steps"
+    sample = (f"{procs} processes x crossed {n_sample}x{n_sample} ({npatch} patches each) of the {args.n}x{args.n} workload, "
+              f"mean of {args.steps} steps, step = slowest process")
     line = {
         "impl": "reference", "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": total,
     }
@@ -344,9 +367,9 @@ def main():
     }
     cpu = None
     if not args.no_cpu:
-        v, npatch_s, dt = time_oracle(args.path, args.cpu_n, k, nrhs, 3)
-        cpu = {"value": v, "unit": "patches/s", "cores": 1, "kind": "port",
-               "sample": f"crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches) of the same workload, min of 3, {os.cpu_count()} host cores present"}
+        v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1)
+        cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": "port",
+               "sample": f"{procs} processes x crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches each) of the same workload, mean of 3 steps"}
     line = {
         "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

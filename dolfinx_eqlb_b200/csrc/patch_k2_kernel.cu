@@ -590,7 +590,7 @@ template <bool EV, int S>
 __global__ void __launch_bounds__(128, 4)
 patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ k2tab, const double* __restrict__ cellJ,
                  int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
-                 const int4* __restrict__ rec, int nfct)
+                 const int4* __restrict__ rec, int nfct, int nwt)
 {
   extern __shared__ double s_mem[];
   double* s_blk = s_mem;
@@ -605,12 +605,20 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
   constexpr int k = 2, nrt = 8;
   const int lane = threadIdx.x & 31;
   const int j = lane % S;  // cell index within the patch / owned chain facet
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int p = warp * PPW + lane / S;
+  // persistent CTAs: every warp walks over warp tiles (32 lane records = PPW patches) with a
+  // grid stride, the tables are staged once per CTA and the record of the next tile is in
+  // flight while the current one is processed
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  int wt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int4 rc_next = (wt < nwt) ? rec[(size_t)wt * 32 + lane] : make_int4(0, 0, 0, 0);
+  for (; wt < nwt; wt += wstride)
+  {
+  const int4 rc = rc_next;
+  if (wt + wstride < nwt)
+    rc_next = rec[(size_t)(wt + wstride) * 32 + lane];
+  const int p = wt * PPW + lane / S;
   const bool valid = p < count;
   const size_t ip = (size_t)first + (valid ? p : 0);
-  // one coalesced 16-byte record per lane (segments are padded with zero records)
-  const int4 rc = rec[(size_t)warp * 32 + lane];
   const int nc = valid ? (rc.y >> 16) : 0;
   const bool active = j < nc;
   const int32_t c = rc.x;
@@ -985,6 +993,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       }
     }
   }
+  }
 }
 
 } // namespace
@@ -1050,11 +1059,14 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
     // warp-cooperative kernel: S lanes per patch
     const size_t smem = (size_t)K2_TAB * sizeof(double);
     const int S = lanes;
-    const int ppb = bs / S;  // patches per block
-    const int grid = (count + ppb - 1) / ppb;
+    const int nwt = (count + (32 / S) - 1) / (32 / S);  // warp tiles
+    static const int waves = getenv("EQLB_K2W_WAVES") ? atoi(getenv("EQLB_K2W_WAVES")) : 1;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * 4 * waves));
     auto kern = (S == 4) ? patch_k2w_kernel<EV, 4> : (S == 8 ? patch_k2w_kernel<EV, 8> : patch_k2w_kernel<EV, 16>);
     kern<<<grid, bs, smem, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p, bstride,
-                                        use_atomics, h->d_prec.p + recoff, h->nfct);
+                                        use_atomics, h->d_prec.p + recoff, h->nfct, nwt);
   }
   else
   {

@@ -98,7 +98,7 @@ template <int K, bool EV, int S>
 __global__ void __launch_bounds__(128, (K == 2 ? 4 : 2))
 patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ tab, const double* __restrict__ cellJ, int nrhs,
                 RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
-                const int4* __restrict__ rec, int nfct)
+                const int4* __restrict__ rec, int nfct, int nwt)
 {
   using D = KW<K>;
   constexpr int B = D::B, nadd = D::nadd, ndiv = D::ndiv, NT = D::NT, NDG = D::NDG, nrt = D::nrt, nact = D::nact,
@@ -116,12 +116,19 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
   constexpr int PPW = 32 / S;
   const int lane = threadIdx.x & 31;
   const int j = lane % S;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int p = warp * PPW + lane / S;
+  // persistent CTAs: grid-stride loop over warp tiles (32 lane records), tables staged once
+  // per CTA, record of the next tile in flight
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  int wt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int4 rc_next = (wt < nwt) ? rec[(size_t)wt * 32 + lane] : make_int4(0, 0, 0, 0);
+  for (; wt < nwt; wt += wstride)
+  {
+  const int4 rc = rc_next;
+  if (wt + wstride < nwt)
+    rc_next = rec[(size_t)(wt + wstride) * 32 + lane];
+  const int p = wt * PPW + lane / S;
   const bool valid = p < count;
   const size_t ip = (size_t)first + (valid ? p : 0);
-  // one coalesced 16-byte record per lane (segments are padded with zero records)
-  const int4 rc = rec[(size_t)warp * 32 + lane];
   const int nc = valid ? (rc.y >> 16) : 0;
   const bool active = j < nc;
   const int32_t c = rc.x;
@@ -952,6 +959,7 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
       }
     }
   }
+  }
 }
 
 template <int K>
@@ -1021,12 +1029,14 @@ void launch_kw_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int 
   const size_t smem = (size_t)D::TAB * sizeof(double);
   if ((S != 4 && S != 8 && S != 16) || recoff < 0)
     throw EqlbError(EQLB_ERR_STATE, "warp-cooperative kernel: segment without lane records");
-  const int ppb = bs / S;
-  const int grid = (count + ppb - 1) / ppb;
+  const int nwt = (count + (32 / S) - 1) / (32 / S);  // warp tiles
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * (K == 2 ? 4 : 2)));
   auto kern = (S == 4) ? patch_kw_kernel<K, EV, 4> : (S == 8 ? patch_kw_kernel<K, EV, 8> : patch_kw_kernel<K, EV, 16>);
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, bs, smem, h->stream>>>(h->patch_view(), first, count, h->d_kwtab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p,
-                                      (size_t)h->ncell * h->nrt, use_atomics, h->d_prec.p + recoff, h->nfct);
+                                      (size_t)h->ncell * h->nrt, use_atomics, h->d_prec.p + recoff, h->nfct, nwt);
   CUDA_CHECK(cudaGetLastError());
   h->launches++;
 }

@@ -306,31 +306,34 @@ def main():
     hF = [torch.from_numpy(f).pin_memory() for f in F]
     hS = [torch.zeros(nout, dtype=torch.float64).pin_memory() for _ in range(nrhs)]
     qG, qF, qS = dptrs(hG), dptrs(hF), dptrs(hS)
-    hprob = prob
-    if world == 1:
-        # the user-facing default for host arrays: staged copy-in / kernels / copy-out
-        cls = eqlb.FluxEqlbSE if args.path == "se" else eqlb.FluxEqlbEV
-        heq = cls(k, m, F, G, host_pipeline=True)
-        heq.set_boundary_conditions(bfct, bcs)
-        hprob = heq.problem
-        hprob.set_stream(stream.cuda_stream)
+    # the user-facing default for host arrays: staged copy-in / kernels / copy-out
+    cls = eqlb.FluxEqlbSE if args.path == "se" else eqlb.FluxEqlbEV
+    heq = cls(k, m, F, G, node_owned=node_owned, host_pipeline=True)
+    heq.set_boundary_conditions(bfct, bcs)
+    hprob = heq.problem
+    hprob.set_stream(stream.cuda_stream)
+
+    def run_host(ps, memspace):
+        if args.path == "se":
+            rc = lib.eqlb_se_run(hprob.h, qG, qF, ps, cabi.c_double_p(), memspace)
+        else:
+            rc = lib.eqlb_ev_run(hprob.h, qG, qF, ps, memspace)
+        if rc != 0:
+            raise RuntimeError(lib.eqlb_last_error().decode())
 
     def step_host():
         if world > 1:
-            for d, h_ in zip(dG + dF + dS, hG + hF + hS):
-                d.copy_(h_, non_blocking=True)
-            step_device()
+            # EQLB_HOST_IN: host inputs staged in, flux stays on the device for the halo sum
+            for d in dS:
+                d.zero_()
+            run_host(pS, 3)
+            hx.apply(dS)
             for d, h_ in zip(dS, hS):
                 h_.copy_(d, non_blocking=True)
             torch.cuda.synchronize()
             return
         # EQLB_HOST_ZEROED: the flux starts from zero as in the reference's equilibrate_fluxes
-        if args.path == "se":
-            rc = lib.eqlb_se_run(hprob.h, qG, qF, qS, cabi.c_double_p(), 2)
-        else:
-            rc = lib.eqlb_ev_run(hprob.h, qG, qF, qS, 2)
-        if rc != 0:
-            raise RuntimeError(lib.eqlb_last_error().decode())
+        run_host(qS, 2)
 
     e2e_steps = max(3, min(args.steps, 5))
     step_host()
@@ -345,8 +348,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF)
-    if world > 1:
-        h2d += sum(s.numel() * 8 for s in hS)
     d2h = sum(s.numel() * 8 for s in hS)
 
     if dist is not None:

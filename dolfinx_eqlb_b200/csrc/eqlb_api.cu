@@ -632,7 +632,7 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
     throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": null argument");
   if (!h->bcs_set)
     throw EqlbError(EQLB_ERR_STATE, std::string(who) + ": call eqlb_set_bcs first");
-  if (memspace != EQLB_HOST && memspace != EQLB_DEVICE && memspace != EQLB_HOST_ZEROED)
+  if (memspace != EQLB_HOST && memspace != EQLB_DEVICE && memspace != EQLB_HOST_ZEROED && memspace != EQLB_HOST_IN)
     throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": unknown memspace");
   const int nrhs = h->nrhs;
   const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg;
@@ -660,14 +660,18 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
     return;
   }
   const bool zeroed = (memspace == EQLB_HOST_ZEROED);
+  const bool sigma_dev = (memspace == EQLB_HOST_IN);
+  if (sigma_dev && korn)
+    throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": EQLB_HOST_IN does not take Korn constants");
   h->d_stage_G.alloc(nG * nrhs);
   h->d_stage_f.alloc(nF * nrhs);
-  h->d_stage_sigma.alloc(nS * nrhs);
+  if (!sigma_dev)
+    h->d_stage_sigma.alloc(nS * nrhs);
   for (int r = 0; r < nrhs; ++r)
   {
     dG[r] = h->d_stage_G.p + r * nG;
     dF[r] = h->d_stage_f.p + r * nF;
-    dS[r] = h->d_stage_sigma.p + r * nS;
+    dS[r] = sigma_dev ? sigma[r] : h->d_stage_sigma.p + r * nS;
   }
   if (korn)
   {
@@ -684,13 +688,13 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
       CUDA_CHECK(cudaMemcpyAsync((void*)dF[r], f[r], nF * 8, cudaMemcpyHostToDevice, h->stream));
       if (zeroed)
         CUDA_CHECK(cudaMemsetAsync(dS[r], 0, nS * 8, h->stream));
-      else
+      else if (!sigma_dev)
         CUDA_CHECK(cudaMemcpyAsync(dS[r], sigma[r], nS * 8, cudaMemcpyHostToDevice, h->stream));
     }
     if (korn)
       CUDA_CHECK(cudaMemcpyAsync(dK, korn, (size_t)h->ncell * 8, cudaMemcpyHostToDevice, h->stream));
     launch();
-    for (int r = 0; r < nrhs; ++r)
+    for (int r = 0; r < nrhs && !sigma_dev; ++r)
       CUDA_CHECK(cudaMemcpyAsync(sigma[r], dS[r], nS * 8, cudaMemcpyDeviceToHost, h->stream));
     if (korn)
       CUDA_CHECK(cudaMemcpyAsync(korn, dK, (size_t)h->ncell * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -721,7 +725,7 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
   {
     if (zeroed)
       CUDA_CHECK(cudaMemsetAsync(dS[r], 0, nS * 8, h->stream));
-    else
+    else if (!sigma_dev)
       CUDA_CHECK(cudaMemcpyAsync(dS[r], sigma[r], nS * 8, cudaMemcpyHostToDevice, h->s_h2d));
   }
   auto cell_lo = [&](int sidx) { return (size_t)((long)h->ncell * sidx / nst); };
@@ -747,6 +751,8 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
       launch();
       CUDA_CHECK(cudaEventRecord(h->ev_done[sidx], h->stream));
       CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[sidx], 0));
+      if (sigma_dev)
+        continue;
       for (const auto& sl : slabs)
         if (sl.final_stage == sidx && sl.len)
           for (int r = 0; r < nrhs; ++r)
@@ -761,6 +767,11 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
   }
   h->win_lo = 0;
   h->win_hi = 1 << 30;
+  if (sigma_dev)
+  {
+    CUDA_CHECK(cudaStreamSynchronize(h->s_h2d));  // the host inputs may be reused; kernels stay queued
+    return;
+  }
   CUDA_CHECK(cudaStreamSynchronize(h->s_d2h));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }

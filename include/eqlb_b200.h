@@ -35,6 +35,10 @@ extern "C" {
  * practice: `FluxEqlbSE.py:79-81` creates zero flux functions and equilibrates into them
  * once), which saves the host->device copy of sigma */
 #define EQLB_HOST_ZEROED 2
+/* G and f are host pointers, sigma is a device pointer (accumulated in place, result stays
+ * on the device, e.g. for the halo sum of a distributed run); returns when the inputs have
+ * been consumed, the kernels are ordered on the handle's stream */
+#define EQLB_HOST_IN 3
 
 #define EQLB_OK 0
 #define EQLB_ERR_INPUT (-1)   /* the reference's std::runtime_error on bad input */

@@ -59,3 +59,33 @@ def test_staged_oracle_parity(monkeypatch):
     ref = po.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
     eq = run(case, "ev", True)
     assert rel_err(eq.list_flux[0], ref[0]) < 1e-10
+
+
+@pytest.mark.parametrize("path", ["se", "ev"])
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_host_inputs_device_result(monkeypatch, path, pipeline):
+    """EQLB_HOST_IN: G, f from host memory, the flux accumulated into a device vector."""
+    import ctypes as C
+
+    import torch
+
+    from dolfinx_eqlb_b200 import cabi
+
+    monkeypatch.setenv("EQLB_PIPE_STAGES", "4")
+    m = make_mesh("crossed", 34, None, perturb=0.2)
+    case = PoissonCase(m, 2, [[1, 3]], seed=5, hom=False)
+    ref = run(case, path, False)
+    eq = run(case, path, pipeline)
+    prob = eq.problem
+    G = [np.ascontiguousarray(g) for g in case.G]
+    F = [np.ascontiguousarray(f) for f in case.F]
+    dS = [torch.ones(ref.list_flux[0].size, dtype=torch.float64, device="cuda")]
+    pS = (cabi.c_double_p * 1)(C.cast(dS[0].data_ptr(), cabi.c_double_p))
+    torch.cuda.synchronize()
+    if path == "se":
+        rc = prob.lib.eqlb_se_run(prob.h, cabi.ptr_array(G), cabi.ptr_array(F), pS, cabi.c_double_p(), 3)
+    else:
+        rc = prob.lib.eqlb_ev_run(prob.h, cabi.ptr_array(G), cabi.ptr_array(F), pS, 3)
+    assert rc == 0, prob.lib.eqlb_last_error().decode()
+    torch.cuda.synchronize()
+    assert rel_err(dS[0].cpu().numpy() - 1.0, ref.list_flux[0]) < 1e-12

@@ -98,7 +98,7 @@ def build_case(n, k, nrhs):
     return m, T, G, F, bfct, bcs
 
 
-def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue):
+def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue, stress=False):
     """One host process = one rank of the reference's MPI-parallel CPU path: it equilibrates
     its own n x n block (no communication: an upper bound of the reference's scaling)."""
     from oracle import pyoracle as po
@@ -107,7 +107,7 @@ def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue):
     m, T, G, F, bfct, bcs = build_case(n, k, nrhs)
     ft = np.stack([ms.facet_types(m, [1, 2, 3, 4], []) for _ in range(nrhs)])
     bc = po.BCData(ft)
-    run = (lambda: po.se_run(m, T, bc, G, F)) if path == "se" else (lambda: po.ev_run(m, T, bc, G, F))
+    run = (lambda: po.se_run(m, T, bc, G, F, stress=stress)) if path == "se" else (lambda: po.ev_run(m, T, bc, G, F))
     for _ in range(warmup):
         run()
     barrier.wait()
@@ -126,7 +126,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None):
+def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None, stress=False):
     """CPU baseline: the oracle restatement (reference loop structure) on a bounded sample
     of the same workload, one process per host core like the reference under mpirun.
     Returns (patches/s over all processes, patches per process, seconds per step, processes)."""
@@ -135,7 +135,7 @@ def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None):
     procs = procs or min(host_cores(), 128)
     ctx = mp.get_context("spawn")
     barrier, queue = ctx.Barrier(procs), ctx.Queue()
-    ws = [ctx.Process(target=_oracle_worker, args=(path, n, k, nrhs, warmup, steps, barrier, queue)) for _ in range(procs)]
+    ws = [ctx.Process(target=_oracle_worker, args=(path, n, k, nrhs, warmup, steps, barrier, queue, stress)) for _ in range(procs)]
     for w in ws:
         w.start()
     res = [queue.get() for _ in ws]
@@ -156,7 +156,7 @@ def reference_arm(args):
         return
     n_sample = args.cpu_n
     t0 = time.perf_counter()
-    value, npatch, sec, procs = time_oracle(args.path, n_sample, args.k, args.nrhs, args.steps, max(args.warmup, 0))
+    value, npatch, sec, procs = time_oracle(args.path, n_sample, args.k, args.nrhs, args.steps, max(args.warmup, 0), stress=args.stress)
     total = time.perf_counter() - t0
     sample = (f"{procs} processes x crossed {n_sample}x{n_sample} ({npatch} patches each) of the {args.n}x{args.n} workload, "
               f"mean of {args.steps} steps, step = slowest process")
@@ -174,6 +174,8 @@ def reference_arm(args):
 
 def workload_config(args):
     name = {"ev": "Poisson FluxEqlbEV, P2 primal / RT2 flux", "se": "Poisson FluxEqlbSE"}[args.path]
+    if getattr(args, "stress", False):
+        name = "Linear elasticity stress equilibration with weak symmetry (FluxEqlbSE)"
     return {
         "workload": f"{name}, degree_flux={args.k}, {args.n}x{args.n} crossed unit square, pure Dirichlet, nrhs={args.nrhs}",
         "path": args.path, "degree_flux": args.k, "n": args.n, "nrhs": args.nrhs,
@@ -194,8 +196,11 @@ def main():
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--cpu-n", type=int, default=256, dest="cpu_n")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--stress", action="store_true", help="SE with weak symmetry: nrhs >= 2 rows of a stress tensor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.stress:
+        args.path, args.nrhs = "se", max(args.nrhs, 2)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -233,7 +238,7 @@ def main():
         bcs = [[] for _ in range(nrhs)]
         npatch_total = nnode_global
     if args.path == "se":
-        eq = eqlb.FluxEqlbSE(k, m, F, G, node_owned=node_owned, host_pipeline=False)
+        eq = eqlb.FluxEqlbSE(k, m, F, G, node_owned=node_owned, host_pipeline=False, equilibrate_stress=args.stress)
         nout = m.ncell * T.nrt
     else:
         eq = eqlb.FluxEqlbEV(k, m, F, G, node_owned=node_owned, host_pipeline=False)
@@ -308,7 +313,8 @@ def main():
     qG, qF, qS = dptrs(hG), dptrs(hF), dptrs(hS)
     # the user-facing default for host arrays: staged copy-in / kernels / copy-out
     cls = eqlb.FluxEqlbSE if args.path == "se" else eqlb.FluxEqlbEV
-    heq = cls(k, m, F, G, node_owned=node_owned, host_pipeline=True)
+    kw = {"equilibrate_stress": True} if args.stress else {}
+    heq = cls(k, m, F, G, node_owned=node_owned, host_pipeline=True, **kw)
     heq.set_boundary_conditions(bfct, bcs)
     hprob = heq.problem
     hprob.set_stream(stream.cuda_stream)
@@ -368,7 +374,7 @@ def main():
     }
     cpu = None
     if not args.no_cpu:
-        v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1)
+        v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress)
         cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": "port",
                "sample": f"{procs} processes x crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches each) of the same workload, mean of 3 steps"}
     line = {

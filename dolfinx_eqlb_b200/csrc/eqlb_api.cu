@@ -678,7 +678,8 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
     h->d_stage_korn.alloc(h->ncell);
     dK = h->d_stage_korn.p;
   }
-  const bool pipelined = h->nchunk > 1 && !(h->flags & (EQLB_FLAG_STRESS | EQLB_FLAG_ATOMIC)) && h->h_group_off.empty()
+  // (grouped boundary patches of the stress path read the accumulated global stress: not staged)
+  const bool pipelined = h->nchunk > 1 && !(h->flags & EQLB_FLAG_ATOMIC) && h->h_group_off.empty()
                          && !korn && h->nseg == h->nchunk * h->ncolours;
   if (!pipelined)
   {

@@ -31,6 +31,10 @@ constexpr int K2_NT = 3;  // cell moments: (0,0), (0,1), (1,0)
 //  local facet pairs read their tables without shared-memory bank conflicts, 16-B aligned)
 constexpr int K2_O_MASS = 0, K2_O_H = 72, K2_O_CMF = 96, K2_O_CMG = 106, K2_O_FM = 124, K2_O_BC = 136, K2_BLOCK = 146;
 constexpr int K2_TAB = 6 * K2_BLOCK + 12;  // + dg_mono [3][3] + mono_int [3]
+// stress (weak symmetry) variant: per-combo block of int phi_q^d lambda_j on the reference cell,
+// [q: lo0 lo1 hi0 hi1 div0 div1][d][j: patch node, outer node of E_a, outer node of E_{a-1}]
+constexpr int K2P_BLOCK = 50;  // 36 used; stride = 2 mod 16 doubles (bank-conflict free across combos)
+constexpr int K2_TAB_STRESS = K2_TAB + 6 * K2P_BLOCK;
 constexpr int K2_SLOTS = 8;                // per patch cell: ip,e,g,w,l of chain facet a+1 ; cz_m, cz_p, ch of cell a
 
 struct K2Cell
@@ -586,8 +590,19 @@ __device__ __forceinline__ double seg_sum(double v)
   return v;
 }
 
-template <bool EV, int S>
-__global__ void __launch_bounds__(128, 4)
+// shared-memory scratch of the weak-symmetry stage per patch (doubles): factor [4][S],
+// X [2][S+1][S+1]; padded to 8 mod 16 so that the patches of a warp use different banks
+template <int S>
+struct K2Stress
+{
+  static constexpr int XROW = S + 1;
+  static constexpr int O_X = 4 * S;
+  static constexpr int RAW = O_X + 2 * (S + 1) * XROW;
+  static constexpr int TILE = RAW + ((8 - RAW % 16) + 16) % 16;
+};
+
+template <bool EV, int S, int MINB, bool STRESS>
+__global__ void __launch_bounds__(128, MINB)
 patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ k2tab, const double* __restrict__ cellJ,
                  int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
                  const int4* __restrict__ rec, int nfct, int nwt)
@@ -596,9 +611,12 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
   double* s_blk = s_mem;
   double* s_dgm = s_mem + 6 * K2_BLOCK;
   double* s_mono = s_dgm + 9;
-  for (int i = threadIdx.x; i < K2_TAB; i += blockDim.x)
+  for (int i = threadIdx.x; i < (STRESS ? K2_TAB_STRESS : K2_TAB); i += blockDim.x)
     s_mem[i] = k2tab[i];
   __syncthreads();
+  [[maybe_unused]] const double* s_p1 = s_mem + K2_TAB;
+  [[maybe_unused]] double* s_tile = s_mem + K2_TAB_STRESS + ((threadIdx.x >> 5) * (32 / S) + (threadIdx.x & 31) / S) * K2Stress<S>::TILE;
+  [[maybe_unused]] double cf0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // stress row 0, kept until row 1 is done
 
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int PPW = 32 / S;
@@ -896,10 +914,10 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       S_ZZ = 1.0;
     if (mark_f0)
       S_FF = 1.0;
-    double u_F = 0.0, u_Z = 0.0;
+    double u_F = 0.0, u_Z = 0.0, idet = 0.0;
     if (valid)
     {
-      const double idet = 1.0 / (S_FF * S_ZZ - S_FZ * S_FZ);
+      idet = 1.0 / (S_FF * S_ZZ - S_FZ * S_FZ);
       u_F = (l_F * S_ZZ - S_FZ * l_Z) * idet;
       u_Z = (S_FF * l_Z - S_FZ * l_F) * idet;
     }
@@ -913,7 +931,8 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
     }
     const double u_next = __shfl_down_sync(FULL, u, 1, S);
 
-    // ---- map back and accumulate ----
+    // ---- map back ----
+    double co[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // corrector of the cell: [lo0 lo1 hi0 hi1 div0 div1]
     if (active)
     {
       const double u_lo = first_c ? u_F : u;
@@ -925,15 +944,258 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
         um0 = t0;
         um1 = t1;
       }
-      const double up0 = p_ea * u_Z, up1 = p_ea * u_hi;
-      const double clo0 = cfv[0] + um0, clo1 = cfv[1] + um1;
-      const double chi0 = cfv[2] + up0, chi1 = cfv[3] + up1;
+      co[0] = cfv[0] + um0;
+      co[1] = cfv[1] + um1;
+      co[2] = cfv[2] + p_ea * u_Z;
+      co[3] = cfv[3] + p_ea * u_hi;
+      co[4] = cfv[4];
+      co[5] = cfv[5];
+    }
+
+    if constexpr (STRESS)
+    {
+      // rows 0/1 of the stress tensor are accumulated after the weak-symmetry correction
+      if (r == 0)
+      {
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          cf0[q] = co[q];
+        continue;
+      }
+      if (r == 1)
+      {
+        // ---- weak symmetry (se/solve_patch_weaksym.hpp:59-233, se/stressmin_kernel.hpp:76-248) for
+        // interior patches: min |tau_0|^2 + |tau_1|^2 over the divergence-free patch space s.t.
+        // (as(sigma + tau), lambda_n) = 0 for the hat functions of all patch nodes.  A is the
+        // matrix just factorised; X = A^-1 B is solved one constraint column per lane, the Schur
+        // complement K = sum_k B_k^T X_k is reduced analytically by the mean-value multiplier
+        // (the columns of B sum to zero on an interior patch) to an nc x nc SPD system. ----
+        using KS = K2Stress<S>;
+        double* Fs = s_tile;            // [4][S]: e*ipv, g*ipv, w*ipv, ipv of the chain rows
+        double* Xs = s_tile + KS::O_X;  // [2][S+1][XROW]
+        Fs[j] = e * ipv;
+        Fs[S + j] = g * ipv;
+        Fs[2 * S + j] = w * ipv;
+        Fs[3 * S + j] = ipv;
+        // moments int_T phi_q^d lambda_n of the cell
+        const double* tp = s_p1 + combo_of(fm, fp) * K2P_BLOCK;
+        const double J00 = sgn * cur.adj[3], J01 = -sgn * cur.adj[1], J10 = -sgn * cur.adj[2], J11 = sgn * cur.adj[0];
+        double Px[4][3], Py[4][3], sj[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+          for (int n = 0; n < 3; ++n)
+          {
+            const double t0 = tp[(q * 2) * 3 + n], t1 = tp[(q * 2 + 1) * 3 + n];
+            const double px = J00 * t0 + J01 * t1, py = J10 * t0 + J11 * t1;
+            sj[n] += cf0[q] * py - co[q] * px;  // (sigma_01 - sigma_10, lambda_n)
+            if (q < 4)
+            {
+              Px[q][n] = px;
+              Py[q][n] = py;
+            }
+          }
+        // patch functions of the cell: lo (higher order on E_a-1), Z (d0), hi (higher order on E_a);
+        // B_0 = (psi_y, lambda), B_1 = -(psi_x, lambda)
+        double blo[2][3], bz[2][3], bhi[2][3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+        {
+          double q0x = Px[0][n], q0y = Py[0][n];
+          if (rev0)
+          {
+            q0x = -q0x - Px[1][n];
+            q0y = -q0y - Py[1][n];
+          }
+          blo[0][n] = p_em * Py[1][n];
+          blo[1][n] = -p_em * Px[1][n];
+          bz[0][n] = p_em * q0y + p_ea * Py[2][n];
+          bz[1][n] = -(p_em * q0x + p_ea * Px[2][n]);
+          bhi[0][n] = p_ea * Py[3][n];
+          bhi[1][n] = -p_ea * Px[3][n];
+        }
+        // lane c owns the outer node N_c of E_c (lo facet of cell c): node slot 2 of cell c and
+        // slot 1 of cell c-1 (cyclic)
+        const int ncs = max(nc, 1);
+        const int prv = (j + ncs - 1) % ncs, nxt = (j + 1) % ncs;
+        double vA[2], vB[2], vC[2], vZ[2];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
+          vA[kk] = __shfl_sync(FULL, blo[kk][1], prv, S);
+          vB[kk] = blo[kk][2] + __shfl_sync(FULL, bhi[kk][1], prv, S);
+          vC[kk] = bhi[kk][2];
+          vZ[kk] = bz[kk][2] + __shfl_sync(FULL, bz[kk][1], prv, S);
+          if (!active)
+            vA[kk] = vB[kk] = vC[kk] = vZ[kk] = 0.0;
+        }
+        const double adet = active ? fabs(cur.det) : 0.0;
+        double Lc = -(sj[2] + __shfl_sync(FULL, sj[1], prv, S));
+        double mN = (adet + __shfl_sync(FULL, adet, prv, S)) * (1.0 / 6.0);
+        if (!active)
+          Lc = mN = 0.0;
+        const double Lc0 = -seg_sum<S>(sj[0]);
+        const double area = 0.5 * seg_sum<S>(adet);
+        const double Lsum = Lc0 + seg_sum<S>(Lc);  // (shuffles stay outside of divergent code)
+        const double mu = valid ? Lsum / area : 0.0;
+        double rhs = -(Lc - mu * mN);
+        __syncwarp();
+        // ---- X[:, N_c] = A^-1 B[:, N_c] for both rows, column c in lane c ----
+        double x[2][S + 1], xZ[2];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
+#pragma unroll
+          for (int b = 0; b < S; ++b)
+            x[kk][b] = (b == prv ? vA[kk] : 0.0) + (b == j ? vB[kk] : 0.0) + (b == nxt ? vC[kk] : 0.0);
+          x[kk][S] = 0.0;
+          xZ[kk] = vZ[kk];
+        }
+#pragma unroll
+        for (int b = 1; b < S; ++b)
+        {
+          const double mp_ = Fs[b - 1], gb = Fs[S + b], wb = Fs[2 * S + b];
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+          {
+            if (b >= 2)
+              x[kk][b] -= mp_ * x[kk][b - 1];
+            x[kk][0] -= gb * x[kk][b];
+            xZ[kk] -= wb * x[kk][b];
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
+          const double xf = x[kk][0], xz = xZ[kk];
+          x[kk][0] = (xf * S_ZZ - S_FZ * xz) * idet;
+          xZ[kk] = (S_FF * xz - S_FZ * xf) * idet;
+        }
+#pragma unroll
+        for (int b = S - 1; b >= 1; --b)
+        {
+          const double mb = Fs[b], gb = Fs[S + b], wb = Fs[2 * S + b], ib = Fs[3 * S + b];
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            x[kk][b] = x[kk][b] * ib - mb * x[kk][b + 1] - gb * x[kk][0] - wb * xZ[kk];
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
+#pragma unroll
+          for (int b = 0; b < S; ++b)
+            Xs[(kk * (S + 1) + b) * KS::XROW + j] = x[kk][b];
+          Xs[(kk * (S + 1) + S) * KS::XROW + j] = xZ[kk];
+        }
+        __syncwarp();
+        // ---- row r = j of K' = sum_k B_k^T X_k (symmetric positive definite) ----
+        double Kr[S];
+#pragma unroll
+        for (int c2 = 0; c2 < S; ++c2)
+        {
+          double acc = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+          {
+            const double* Xk = Xs + kk * (S + 1) * KS::XROW + c2;
+            acc += vA[kk] * Xk[prv * KS::XROW] + vB[kk] * Xk[j * KS::XROW] + vC[kk] * Xk[nxt * KS::XROW]
+                   + vZ[kk] * Xk[S * KS::XROW];
+          }
+          Kr[c2] = acc;
+        }
+        if (!active)
+        {
+#pragma unroll
+          for (int c2 = 0; c2 < S; ++c2)
+            Kr[c2] = (c2 == j) ? 1.0 : 0.0;
+          rhs = 0.0;
+        }
+        // ---- K' w = rhs: Gaussian elimination without pivoting, row r in lane r ----
+        double myip = 1.0;
+#pragma unroll
+        for (int pv_ = 0; pv_ < S; ++pv_)
+        {
+          const double piv = __shfl_sync(FULL, Kr[pv_], pv_, S);
+          const double ip = 1.0 / piv;
+          if (j == pv_)
+            myip = ip;
+          if (pv_ < S - 1)
+          {
+            const double prhs = __shfl_sync(FULL, rhs, pv_, S);
+            const double lfac = (j > pv_) ? Kr[pv_] * ip : 0.0;
+            rhs -= lfac * prhs;
+#pragma unroll
+            for (int c2 = pv_ + 1; c2 < S; ++c2)
+              Kr[c2] -= lfac * __shfl_sync(FULL, Kr[c2], pv_, S);
+          }
+        }
+        double wv[S];
+#pragma unroll
+        for (int pv_ = S - 1; pv_ >= 0; --pv_)
+        {
+          wv[pv_] = __shfl_sync(FULL, rhs * myip, pv_, S);
+          if (j < pv_)
+            rhs -= Kr[pv_] * wv[pv_];
+        }
+        // ---- tau_k = -X_k w on the own facet row and on d0; correct both rows ----
+        double ub[2], uz[2];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
+          const double* Xk = Xs + kk * (S + 1) * KS::XROW;
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int c2 = 0; c2 < S; ++c2)
+          {
+            a0 -= Xk[j * KS::XROW + c2] * wv[c2];
+            a1 -= Xk[S * KS::XROW + c2] * wv[c2];
+          }
+          ub[kk] = a0;
+          uz[kk] = a1;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
+          const double uhi = __shfl_sync(FULL, ub[kk], nxt, S);
+          if (active)
+          {
+            double um0 = p_em * uz[kk], um1 = p_em * ub[kk];
+            if (rev0)
+            {
+              const double t0 = -um0, t1 = -um0 + um1;
+              um0 = t0;
+              um1 = t1;
+            }
+            double* tgt = kk ? co : cf0;
+            tgt[0] += um0;
+            tgt[1] += um1;
+            tgt[2] += p_ea * uz[kk];
+            tgt[3] += p_ea * uhi;
+          }
+        }
+        __syncwarp();
+        if (active)
+        {
+          double* d0 = ptrs.S[0] + (size_t)c * nrt;
+          atomicAdd(d0 + fm * 2, cf0[0]);
+          atomicAdd(d0 + fm * 2 + 1, cf0[1]);
+          atomicAdd(d0 + fp * 2, cf0[2]);
+          atomicAdd(d0 + fp * 2 + 1, cf0[3]);
+          atomicAdd(d0 + 6, cf0[4]);
+          atomicAdd(d0 + 7, cf0[5]);
+        }
+      }
+    }
+
+    // ---- accumulate ----
+    if (active)
+    {
       if (EV)
       {
         for (int side = (first_c && !internal) ? 0 : 1; side < 2; ++side)
         {
           const bool refl = (info & (side ? 512 : 256)) != 0;
-          const double cl0 = side ? chi0 : clo0, cl1 = side ? chi1 : clo1;
+          const double cl0 = side ? co[2] : co[0], cl1 = side ? co[3] : co[1];
           const double cg0 = refl ? -cl0 : cl0;
           const double cg1 = refl ? (-cl0 + cl1) : cl1;
           double* d = sig + (size_t)(side ? rc.w : rc.z) * k;
@@ -953,14 +1215,14 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
         double* dstc = sig + (size_t)nfct * k + (size_t)c * 2;
         if (use_atomics)
         {
-          atomicAdd(dstc, cfv[4]);
-          atomicAdd(dstc + 1, cfv[5]);
+          atomicAdd(dstc, co[4]);
+          atomicAdd(dstc + 1, co[5]);
         }
         else
         {
           double2 vv = *reinterpret_cast<double2*>(dstc);
-          vv.x += cfv[4];
-          vv.y += cfv[5];
+          vv.x += co[4];
+          vv.y += co[5];
           *reinterpret_cast<double2*>(dstc) = vv;
         }
       }
@@ -969,23 +1231,23 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
         double* d = sig + (size_t)c * nrt;
         if (use_atomics)
         {
-          atomicAdd(d + fm * 2, clo0);
-          atomicAdd(d + fm * 2 + 1, clo1);
-          atomicAdd(d + fp * 2, chi0);
-          atomicAdd(d + fp * 2 + 1, chi1);
-          atomicAdd(d + 6, cfv[4]);
-          atomicAdd(d + 7, cfv[5]);
+          atomicAdd(d + fm * 2, co[0]);
+          atomicAdd(d + fm * 2 + 1, co[1]);
+          atomicAdd(d + fp * 2, co[2]);
+          atomicAdd(d + fp * 2 + 1, co[3]);
+          atomicAdd(d + 6, co[4]);
+          atomicAdd(d + 7, co[5]);
         }
         else
         {
           double2* d2 = reinterpret_cast<double2*>(d);
           double2 vlo = d2[fm], vhi = d2[fp], vdv = d2[3];
-          vlo.x += clo0;
-          vlo.y += clo1;
-          vhi.x += chi0;
-          vhi.y += chi1;
-          vdv.x += cfv[4];
-          vdv.y += cfv[5];
+          vlo.x += co[0];
+          vlo.y += co[1];
+          vhi.x += co[2];
+          vhi.y += co[3];
+          vdv.x += co[4];
+          vdv.y += co[5];
           d2[fm] = vlo;
           d2[fp] = vhi;
           d2[3] = vdv;
@@ -1001,7 +1263,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
 // gather the reference tables per local facet pair (fm, fp); v = 3 - fm - fp
 void build_k2_tables(eqlb_handle* h, const eqlb_tables* t)
 {
-  std::vector<double> tab(K2_TAB, 0.0);
+  std::vector<double> tab(K2_TAB_STRESS, 0.0);
   const int nrt = 8, ndg = 3, nt = 3, k = 2;
   for (int fm = 0; fm < 3; ++fm)
     for (int fp = 0; fp < 3; ++fp)
@@ -1026,6 +1288,15 @@ void build_k2_tables(eqlb_handle* h, const eqlb_tables* t)
           for (int d = 0; d < 2; ++d)
             blk[K2_O_CMG + (tt * 3 + i) * 2 + d] = t->cell_mom_g[(((size_t)v * nt + tt) * ndg + i) * 2 + d];
         }
+      // weak symmetry: int phi_q^d lambda_n, nodes ordered (patch node, outer node of E_a, outer node of E_a-1)
+      {
+        double* pb = tab.data() + K2_TAB + combo_of(fm, fp) * K2P_BLOCK;
+        const int vl[3] = {v, fm, fp};
+        for (int q = 0; q < 6; ++q)
+          for (int d = 0; d < 2; ++d)
+            for (int n = 0; n < 3; ++n)
+              pb[(q * 2 + d) * 3 + n] = t->rt_p1[((size_t)rdof(q) * 2 + d) * 3 + vl[n]];
+      }
       for (int side = 0; side < 2; ++side)
       {
         const int f = side ? fp : fm;
@@ -1047,7 +1318,7 @@ void build_k2_tables(eqlb_handle* h, const eqlb_tables* t)
 
 template <bool EV>
 static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf, int lanes,
-                            int64_t recoff)
+                            int64_t recoff, bool stress)
 {
   if (count <= 0)
     return;
@@ -1063,8 +1334,30 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
     static const int waves = getenv("EQLB_K2W_WAVES") ? atoi(getenv("EQLB_K2W_WAVES")) : 1;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * 4 * waves));
-    auto kern = (S == 4) ? patch_k2w_kernel<EV, 4> : (S == 8 ? patch_k2w_kernel<EV, 8> : patch_k2w_kernel<EV, 16>);
+    if (stress)
+    {
+      // SE with the weak-symmetry stage fused in (interior patches)
+      if constexpr (!EV)
+      {
+        constexpr int minb = 3;
+        const int tile = (S == 4) ? K2Stress<4>::TILE : (S == 8 ? K2Stress<8>::TILE : K2Stress<16>::TILE);
+        const size_t smem_s = ((size_t)K2_TAB_STRESS + (size_t)(bs / S) * tile) * sizeof(double);
+        auto kern = (S == 4) ? patch_k2w_kernel<false, 4, minb, true>
+                             : (S == 8 ? patch_k2w_kernel<false, 8, minb, true> : patch_k2w_kernel<false, 16, minb, true>);
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * minb));
+        kern<<<grid, bs, smem_s, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p, bstride,
+                                              1, h->d_prec.p + recoff, h->nfct, nwt);
+      }
+      CUDA_CHECK(cudaGetLastError());
+      h->launches++;
+      return;
+    }
+    // 5 CTAs/SM (<= 96 registers) measured best on B200: 3 -> 0.87, 4 -> 0.77, 5 -> 0.76, 6 -> 0.75/0.81 ms (EV/SE)
+    constexpr int minb = 5;
+    auto kern = (S == 4) ? patch_k2w_kernel<EV, 4, minb, false>
+                         : (S == 8 ? patch_k2w_kernel<EV, 8, minb, false> : patch_k2w_kernel<EV, 16, minb, false>);
+    const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * minb * waves));
     kern<<<grid, bs, smem, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p, bstride,
                                         use_atomics, h->d_prec.p + recoff, h->nfct, nwt);
   }
@@ -1081,10 +1374,12 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
 }
 
 void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf, int lanes,
-               int64_t recoff)
+               int64_t recoff, bool stress)
 {
+  if (stress && (ev || lanes <= 0 || recoff < 0 || h->nrhs < 2))
+    throw EqlbError(EQLB_ERR_STATE, "degree-2 stress kernel: needs SE, lane records and at least two rows");
   if (ev)
-    launch_k2_range<true>(h, ptrs, first, count, use_atomics, maxnf, lanes, recoff);
+    launch_k2_range<true>(h, ptrs, first, count, use_atomics, maxnf, lanes, recoff, false);
   else
-    launch_k2_range<false>(h, ptrs, first, count, use_atomics, maxnf, lanes, recoff);
+    launch_k2_range<false>(h, ptrs, first, count, use_atomics, maxnf, lanes, recoff, stress);
 }

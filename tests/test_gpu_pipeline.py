@@ -89,3 +89,20 @@ def test_host_inputs_device_result(monkeypatch, path, pipeline):
     assert rc == 0, prob.lib.eqlb_last_error().decode()
     torch.cuda.synchronize()
     assert rel_err(dS[0].cpu().numpy() - 1.0, ref.list_flux[0]) < 1e-12
+
+
+def test_staged_stress(monkeypatch):
+    """The weak-symmetry stage is patch local, so the stress path is staged as well."""
+    from test_gpu_stress import elasticity_case
+
+    monkeypatch.setenv("EQLB_PIPE_STAGES", "5")
+    m = make_mesh("crossed", 36, None, perturb=0.2)
+    T, G, f, bfp, bcs, neu = elasticity_case(m, 2, [], seed=3, galerkin=False)
+    res = []
+    for pipeline in (False, True):
+        eq = eqlb.FluxEqlbSE(2, m, f, G, equilibrate_stress=True, host_pipeline=pipeline)
+        eq.set_boundary_conditions(bfp, bcs)
+        eq.equilibrate_fluxes()
+        res.append(eq.list_flux)
+    for r in range(2):
+        assert rel_err(res[1][r], res[0][r]) < 1e-11

@@ -621,6 +621,52 @@ int eqlb_get_se_dofmaps(eqlb_handle* h, int32_t* dofmap, int32_t* projflux_fct, 
       });
 }
 
+int eqlb_get_ev_dofmaps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t* fcts, int8_t* inodes_local, int32_t* dofs_elmt,
+                        int32_t* dofs_patch, int32_t* dofs_global, int32_t* list_patch, int32_t* list_global)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_get_ev_dofmaps: call eqlb_set_bcs first");
+        if (h->ncmax > EQLB_NCMAX)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_get_ev_dofmaps: more than 16 cells around a vertex");
+        const size_t np = h->nnode, ncm = h->ncmax, nz = h->nrt + h->ndg - h->k;
+        const size_t lenf = ncm * (h->nrt - 3 * h->k) + (ncm + 1) * h->k;
+        DevBuf<int32_t> b_nc, b_c, b_f, b_e, b_p, b_g, b_lp, b_lg;
+        DevBuf<int8_t> b_i;
+        auto prep = [&](auto& buf, size_t n)
+        {
+          buf.alloc(n);
+          CUDA_CHECK(cudaMemsetAsync(buf.p, 0xFF, n * sizeof(*buf.p), h->stream));
+        };
+        prep(b_nc, np);
+        prep(b_c, np * ncm);
+        prep(b_f, np * (ncm + 1));
+        prep(b_i, np * ncm);
+        prep(b_e, np * ncm * nz);
+        prep(b_p, np * ncm * nz);
+        prep(b_g, np * ncm * nz);
+        prep(b_lp, np * lenf);
+        prep(b_lg, np * lenf);
+        launch_ev_dofmaps(h, b_nc.p, b_c.p, b_f.p, b_i.p, b_e.p, b_p.p, b_g.p, b_lp.p, b_lg.p);
+        auto fetch = [&](auto* dst, auto& buf)
+        {
+          if (dst)
+            CUDA_CHECK(cudaMemcpy(dst, buf.p, buf.n * sizeof(*buf.p), cudaMemcpyDeviceToHost));
+        };
+        fetch(ncells, b_nc);
+        fetch(cells, b_c);
+        fetch(fcts, b_f);
+        fetch(inodes_local, b_i);
+        fetch(dofs_elmt, b_e);
+        fetch(dofs_patch, b_p);
+        fetch(dofs_global, b_g);
+        fetch(list_patch, b_lp);
+        fetch(list_global, b_lg);
+      });
+}
+
 // Common driver of eqlb_se_run / eqlb_ev_run: device pointers are used in place; host
 // pointers are staged, either in one piece or - with EQLB_FLAG_HOST_PIPELINE - stage by
 // stage on three streams so that both PCIe directions and the SMs work at the same time.

@@ -228,6 +228,8 @@ void launch_compute_cellJ(eqlb_handle* h);
 void launch_patch_builder(eqlb_handle* h, int32_t* d_ncells_out, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inodes,
                           int8_t* d_fcts_local, int8_t* d_type, uint8_t* d_reversed, uint8_t* d_reversion);
 void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, int8_t* d_bmarkers, int ndpc, int hzmax);
+void launch_ev_dofmaps(eqlb_handle* h, int32_t* d_ncells, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inod, int32_t* d_elmt,
+                       int32_t* d_patch, int32_t* d_global, int32_t* d_lpatch, int32_t* d_lglobal);
 void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn);
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma);
 void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* const* dout);

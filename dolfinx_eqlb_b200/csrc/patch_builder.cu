@@ -512,6 +512,203 @@ __global__ void cellJ_kernel(int ncell, const double* __restrict__ x, const int3
   out[1] = make_double2(x[3 * n1 + 1] - y0, x[3 * n2 + 1] - y0);  // J10 J11
 }
 
+
+// ---------------------------------------------------------------------------
+// EV patch ordering and sub-DOF maps (ev/Patch.cpp:83-309, 360-437, 482-676).
+// Parity evidence only: the EV hot kernel works on the SE fan and the conforming
+// global numbering directly.  The EV convention differs from the SE one: the fan
+// starts at the first facet of node->facet (interior) or at the flux / Dirichlet
+// boundary facet, cells are stored 0-based and the interior patch stores the cell
+// BEHIND facet ii at ii+1 (wrap to 0).
+//   mixed element dofs: [3k facet][k^2-k cell flux][ndg DG]; global numbering of the
+//   conforming space: facet*k + j | nfct*k + cell*(k^2-k) + i | nflux + cell*ndg + q.
+// ---------------------------------------------------------------------------
+__global__ void ev_dofmap_kernel(MeshView m, const int8_t* __restrict__ facet_type, int npatch, int ncmax, int k, int nrt,
+                                 int ndg, const uint8_t* __restrict__ owned, int32_t* __restrict__ o_ncells,
+                                 int32_t* __restrict__ o_cells, int32_t* __restrict__ o_fcts, int8_t* __restrict__ o_inod,
+                                 int32_t* __restrict__ o_elmt, int32_t* __restrict__ o_patch, int32_t* __restrict__ o_global,
+                                 int32_t* __restrict__ o_lpatch, int32_t* __restrict__ o_lglobal)
+{
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= npatch || (owned && !owned[node]))
+    return;
+  const int nc = m.node_cell_off[node + 1] - m.node_cell_off[node];
+  const int nf = m.node_fct_off[node + 1] - m.node_fct_off[node];
+  const int32_t* pf = m.node_fct + m.node_fct_off[node];
+  const int nflux_cell = nrt - 3 * k, ndof_cell = nflux_cell + ndg, nz = nrt + ndg - k;
+  const int nflux = m.nfct * k + m.ncell * nflux_cell;
+  const int lenf = ncmax * nflux_cell + (ncmax + 1) * k;
+  int32_t* cells = o_cells + (size_t)node * ncmax;
+  int32_t* fcts = o_fcts + (size_t)node * (ncmax + 1);
+  int8_t* inod = o_inod + (size_t)node * ncmax;
+  int32_t* d_el = o_elmt + (size_t)node * ncmax * nz;
+  int32_t* d_pa = o_patch + (size_t)node * ncmax * nz;
+  int32_t* d_gl = o_global + (size_t)node * ncmax * nz;
+  int32_t* l_pa = o_lpatch + (size_t)node * lenf;
+  int32_t* l_gl = o_lglobal + (size_t)node * lenf;
+  o_ncells[node] = nc;
+
+  // sorted facet ids of the patch (insertion sort, <= 17 entries)
+  int32_t srt[EQLB_NCMAX + 1];
+  for (int i = 0; i < nf; ++i)
+  {
+    int32_t v = pf[i];
+    int q = i;
+    while (q > 0 && srt[q - 1] > v)
+    {
+      srt[q] = srt[q - 1];
+      --q;
+    }
+    srt[q] = v;
+  }
+  auto in_patch = [&](int32_t f)
+  {
+    for (int i = 0; i < nf; ++i)
+      if (srt[i] == f)
+        return true;
+    return false;
+  };
+  // patch type of RHS 0 and first facet
+  const bool bnd = nf > nc;
+  int32_t fct_i = pf[0];
+  if (bnd)
+  {
+    int32_t ef = -1, ep = -1;
+    for (int i = 0; i < nf; ++i)
+    {
+      const int8_t ft = facet_type[pf[i]];
+      if (ft == EQLB_FCT_ESSNT_PRIMAL && ep < 0)
+        ep = pf[i];
+      else if (ft == EQLB_FCT_ESSNT_DUAL && ef < 0)
+        ef = pf[i];
+    }
+    fct_i = (ef < 0) ? ep : ef;
+  }
+  auto gdof = [&](int32_t cell, int ldof) -> int32_t
+  {
+    if (ldof < 3 * k)
+      return m.cell_fct[3 * cell + ldof / k] * k + ldof % k;
+    if (ldof < nrt)
+      return m.nfct * k + cell * nflux_cell + (ldof - 3 * k);
+    return nflux + cell * ndg + (ldof - nrt);
+  };
+  int32_t cell_i = -1, dof_patch = 0, offs_l = 0;
+  for (int ii = 0; ii < nc; ++ii)
+  {
+    // cell behind facet ii and the local ids of that facet in both cells
+    const int o = m.fct_cell_off[fct_i];
+    int32_t c_new, c_old;
+    if (bnd && ii == 0)
+    {
+      c_new = m.fct_cell[o];
+      c_old = c_new;
+    }
+    else if (m.fct_cell[o] == cell_i)
+    {
+      c_new = m.fct_cell[o + 1];
+      c_old = m.fct_cell[o];
+    }
+    else
+    {
+      c_new = m.fct_cell[o];
+      c_old = m.fct_cell[o + 1];
+    }
+    const int lf_new = local_index3(m.cell_fct + 3 * c_new, fct_i);
+    const int lf_old = local_index3(m.cell_fct + 3 * c_old, fct_i);
+    const int8_t vloc = (int8_t)local_index3(m.cell_node + 3 * c_new, node);
+    // next facet: of the two other facets of the cell the one that belongs to the patch
+    const int32_t* cf = m.cell_fct + 3 * c_new;
+    const int32_t fa = cf[lf_new == 0 ? 1 : 0], fb = cf[lf_new == 2 ? 1 : 2];
+    const int32_t e0 = min(fa, fb), e1 = max(fa, fb);
+    int32_t fct_next;
+    if (e0 < srt[0])
+      fct_next = e1;
+    else if (e1 > srt[nf - 1])
+      fct_next = e0;
+    else
+      fct_next = in_patch(e0) ? e0 : e1;
+    // storage position of the cell and offsets of its dof block
+    int32_t offs_p, offs_f;
+    if (bnd)
+    {
+      cells[ii] = c_new;
+      inod[ii] = vloc;
+      offs_f = (ii == 0) ? k : (ii - 1) * nz + k;
+      offs_p = ii * nz;
+    }
+    else if (ii < nf - 1)
+    {
+      cells[ii + 1] = c_new;
+      cells[ii] = c_old;
+      inod[ii + 1] = vloc;
+      offs_f = ii * nz + k;
+      offs_p = (ii + 1) * nz;
+    }
+    else
+    {
+      cells[0] = c_new;
+      inod[0] = vloc;
+      offs_f = ii * nz + k;
+      offs_p = 0;
+    }
+    cell_i = c_new;
+    for (int jj = 0; jj < k; ++jj)
+    {
+      const int ldof = lf_new * k + jj;
+      const int32_t g = gdof(cell_i, ldof);
+      d_el[offs_p] = ldof;
+      d_el[offs_f + jj] = lf_old * k + jj;
+      d_pa[offs_p] = dof_patch;
+      d_pa[offs_f + jj] = dof_patch;
+      d_gl[offs_p] = g;
+      d_gl[offs_f + jj] = g;
+      l_pa[offs_l] = dof_patch;
+      l_gl[offs_l] = g;
+      ++dof_patch;
+      ++offs_p;
+      ++offs_l;
+    }
+    offs_p += k;
+    for (int jj = 0; jj < ndof_cell; ++jj)
+    {
+      const int ldof = 3 * k + jj;
+      const int32_t g = gdof(cell_i, ldof);
+      d_el[offs_p] = ldof;
+      d_pa[offs_p] = dof_patch;
+      d_gl[offs_p] = g;
+      if (jj < nflux_cell)
+      {
+        l_pa[offs_l] = dof_patch;
+        l_gl[offs_l] = g;
+        ++offs_l;
+      }
+      ++dof_patch;
+      ++offs_p;
+    }
+    fcts[ii] = fct_i;
+    fct_i = fct_next;
+  }
+  if (bnd)
+  {
+    const int lf = local_index3(m.cell_fct + 3 * cell_i, fct_i);
+    int32_t offs_p = (nc - 1) * nz + k;
+    for (int jj = 0; jj < k; ++jj)
+    {
+      const int ldof = lf * k + jj;
+      const int32_t g = gdof(cell_i, ldof);
+      d_el[offs_p] = ldof;
+      d_pa[offs_p] = dof_patch;
+      d_gl[offs_p] = g;
+      l_pa[offs_l] = dof_patch;
+      l_gl[offs_l] = g;
+      ++dof_patch;
+      ++offs_p;
+      ++offs_l;
+    }
+    fcts[nf - 1] = fct_i;
+  }
+}
+
 } // namespace
 
 MeshView eqlb_handle::mesh_view() const
@@ -572,6 +769,20 @@ void launch_patch_builder(eqlb_handle* h, int32_t* x_ncells, int32_t* x_cells, i
       h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nactive, h->pstride, h->ncmax,
       expand ? nullptr : h->d_pnode.p, h->d_pncells.p, expand ? nullptr : h->d_pcell.p, h->d_pinfo.p,
       expand ? nullptr : h->d_prhs.p, expand ? nullptr : h->d_prec.p, h->d_seginfo.p, h->nseg, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->launches++;
+}
+
+void launch_ev_dofmaps(eqlb_handle* h, int32_t* d_ncells, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inod, int32_t* d_elmt,
+                       int32_t* d_patch, int32_t* d_global, int32_t* d_lpatch, int32_t* d_lglobal)
+{
+  DevBuf<uint8_t> d_owned;
+  d_owned.upload(h->h_owned.data(), h->h_owned.size());
+  const int bs = 128;
+  ev_dofmap_kernel<<<(h->nnode + bs - 1) / bs, bs, 0, h->stream>>>(h->mesh_view(), h->d_facet_type.p, h->nnode, h->ncmax, h->k,
+                                                                  h->nrt, h->ndg, d_owned.p, d_ncells, d_cells, d_fcts, d_inod,
+                                                                  d_elmt, d_patch, d_global, d_lpatch, d_lglobal);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->launches++;

@@ -190,6 +190,31 @@ class _Problem:
         return dict(dofmap=dm, projflux_fct=pf, bmarkers=bm)
 
 
+    def ev_dofmaps(self):
+        """EV patch ordering + sub-DOF maps (`ev/Patch.cpp:482-676`) of all patches, built on the device."""
+        npatch, ncmax, _ = self.patch_dims()
+        T = self.tables
+        nz = T.nrt + T.ndg - T.k
+        lenf = ncmax * (T.k * T.k - T.k) + (ncmax + 1) * T.k
+        out = dict(
+            ncells=np.zeros(npatch, np.int32), cells=np.zeros((npatch, ncmax), np.int32),
+            fcts=np.zeros((npatch, ncmax + 1), np.int32), inodes_local=np.zeros((npatch, ncmax), np.int8),
+            dofs_elmt=np.zeros((npatch, ncmax * nz), np.int32), dofs_patch=np.zeros((npatch, ncmax * nz), np.int32),
+            dofs_global=np.zeros((npatch, ncmax * nz), np.int32), list_patch=np.zeros((npatch, lenf), np.int32),
+            list_global=np.zeros((npatch, lenf), np.int32),
+        )
+        p32 = lambda a: a.ctypes.data_as(cabi.c_int32_p)
+        _check(
+            self.lib,
+            self.lib.eqlb_get_ev_dofmaps(
+                self.h, p32(out["ncells"]), p32(out["cells"]), p32(out["fcts"]), out["inodes_local"].ctypes.data_as(cabi.c_int8_p),
+                p32(out["dofs_elmt"]), p32(out["dofs_patch"]), p32(out["dofs_global"]), p32(out["list_patch"]),
+                p32(out["list_global"]),
+            ),
+        )
+        return out
+
+
 def _as_ptr_list(arrs):
     return [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
 

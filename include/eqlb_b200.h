@@ -160,6 +160,17 @@ int eqlb_get_patch_maps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t
 int eqlb_get_se_dofmaps(eqlb_handle* h, int32_t* dofmap, int32_t* projflux_fct,
                         int8_t* bmarkers, int32_t* ndpc, int32_t* hzmax);
 
+/* EV patch ordering and sub-DOF maps of the mixed RT_k x DG_(k-1) patch problem
+ * (`ev/Patch.cpp:83-309` ordering, `:482-676` create_subdofmap), EV storage convention;
+ * nz = nrt + ndg - k non-zero element DOFs per patch cell.  HOST buffers, -1 padded:
+ *   ncells [npatch], cells/inodes_local [npatch*ncmax], fcts [npatch*(ncmax+1)],
+ *   dofs_elmt/dofs_patch/dofs_global [npatch*ncmax*nz]   (_dofsnz_elmt/_patch/_global)
+ *   list_patch/list_global [npatch*(ncmax*(k*k-k) + (ncmax+1)*k)] (_list_dofsnz_*_fluxhdiv)
+ * global numbering: facet*k+j | nfct*k + cell*(k*k-k) + i | nflux + cell*ndg + q */
+int eqlb_get_ev_dofmaps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t* fcts, int8_t* inodes_local,
+                        int32_t* dofs_elmt, int32_t* dofs_patch, int32_t* dofs_global,
+                        int32_t* list_patch, int32_t* list_global);
+
 /* number of kernel launches issued by this handle so far (bench "gpu_launches") */
 int64_t eqlb_launch_count(eqlb_handle* h);
 

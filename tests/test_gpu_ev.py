@@ -66,3 +66,23 @@ def test_ev_random_data_neumann():
     ref = po.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
     eq = run_gpu(case)
     assert rel_err(eq.list_flux[0], ref[0]) < RTOL
+
+
+@pytest.mark.parametrize("kind,n,scramble", [("crossed", 4, None), ("crossed", 5, 3), ("randdiag", 6, 2)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("nsets", [[[]], [[1, 4], [1, 3]]])
+def test_ev_dofmaps_bit_exact(kind, n, scramble, k, nsets):
+    """EV patch ordering and sub-DOF maps (ev/Patch.cpp:83-309, 482-676) built on the device
+    are bit-exact against the oracle, patch by patch."""
+    from oracle import pyoracle as po
+
+    m = make_mesh(kind, n, scramble, perturb=0.25)
+    case = PoissonCase(m, k, nsets, seed=1, hom=True)
+    eq = eqlb.FluxEqlbEV(case.k, case.mesh, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    got = eq.problem.ev_dofmaps()
+    for z in range(m.nnode):
+        ref = po.ev_patch_maps(m, case.T, case.oracle_bc(), z)
+        assert got["ncells"][z] == ref["ncells"]
+        for key in ("cells", "fcts", "inodes_local", "dofs_elmt", "dofs_patch", "dofs_global", "list_patch", "list_global"):
+            assert np.array_equal(got[key][z], ref[key]), (z, key)

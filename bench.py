@@ -79,6 +79,15 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+# ncu evidence of the dominant kernel (profiles/README.md), keyed by (path, k, nrhs, stress) at n = 1024:
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the colour launches of one step) and
+# executed FP64 flop per patch (2*dfma + dmul + dadd, predicated-on thread instructions)
+NCU = {
+    ("ev", 2, 1, False): {"traffic": 795.7e6, "flop_per_patch": 2897.0, "capture": "profiles/r1c_ev_k2w_ncu_full_summary.txt"},
+}
+FP64_PEAK_TFLOPS = 36.4  # measured FMA peak of this pool's B200 (profiles/peaks.cu, profiles/peaks_b200.txt)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -366,12 +375,20 @@ def main():
     bpc = alg_bytes_per_cell(k, T.ndg, T.nrt, nrhs, args.path)
     alg_bytes_step = bpc * m.ncell  # per rank
     achieved = alg_bytes_step / (ms_step * 1e-3) / 1e9
+    ncu = NCU.get((args.path, k, nrhs, bool(args.stress))) if (args.n == 1024 and world == 1) else None
+    lps = launches / args.steps
     roof = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "kernel": "se_patch_kernel" if args.path == "se" else "ev_patch_kernel",
-        "alg_bytes_per_patch": bpc * m.ncell / m.nnode, "peak_source": peak_src,
-        "launches_per_step": launches / args.steps,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": ncu["traffic"] if ncu else None,
+        "kernel": "patch_k2w_kernel" if k == 2 else ("patch_kw_kernel" if k == 3 else "patch_kernel"),
+        "alg_bytes_per_patch": bpc * m.ncell / m.nnode, "alg_bytes_per_launch": alg_bytes_step / lps,
+        "avg_launch_ms": ms_step / lps, "peak_source": peak_src, "launches_per_step": lps,
     }
+    if ncu:
+        tf = ncu["flop_per_patch"] * m.nnode / (ms_step * 1e-3) / 1e12
+        roof["fp64"] = {"achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+                        "flop_per_patch": ncu["flop_per_patch"], "source": ncu["capture"],
+                        "note": "executed FP64 flop (ncu) / step time; the kernel is FP64/issue bound, see DESIGN.md section 4"}
     cpu = None
     if not args.no_cpu:
         v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress)

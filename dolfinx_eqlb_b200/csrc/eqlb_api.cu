@@ -8,6 +8,8 @@
 #include <cstring>
 #include <memory>
 
+#include <chrono>
+
 #include "eqlb_internal.cuh"
 
 static thread_local std::string g_last_error;
@@ -48,6 +50,22 @@ void require_device()
 // Greedy vertex colouring such that two patches of one colour never share a cell
 // (two vertices of a common cell get different colours).  Deterministic: vertices
 // in ascending order, smallest free colour.
+// wall-clock breakdown of the setup calls on stderr when EQLB_TIMING is set
+struct StageTimer
+{
+  const bool on = getenv("EQLB_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what)
+  {
+    if (!on)
+      return;
+    cudaDeviceSynchronize();
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[eqlb timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 void colour_patches(eqlb_handle* h)
 {
   const int n = h->nnode;
@@ -231,7 +249,9 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         if (ncmax > EQLB_NCMAX)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_b200: patches with more than " + std::to_string(EQLB_NCMAX)
                                               + " cells are not supported");
+        StageTimer tm;
         require_device();
+        tm.lap("create: device check");
 
         std::unique_ptr<eqlb_handle> h(new eqlb_handle());
         CUDA_CHECK(cudaGetDevice(&h->device));
@@ -269,6 +289,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->d_node_fct_off.upload(mesh->node_fct_off, nn + 1);
         h->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
         h->d_fct_perms.upload(mesh->fct_perms, nc * 3);
+        tm.lap("create: mesh upload");
         h->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
         h->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
         h->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
@@ -277,6 +298,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
         h->h_grouped.assign(nn, 0);
 
+        tm.lap("create: host copies");
         // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
         h->dg_identity = true;
         if (mesh->dg_dofmap)
@@ -291,6 +313,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
             h->d_dg_dofmap.upload(mesh->dg_dofmap, nc * t->ndg);
         }
 
+        tm.lap("create: dg dofmap check");
         // reference-matrix tables -> one flat device block
         std::vector<double> flat;
         TableView& tv = h->tv;
@@ -366,12 +389,17 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
           h->d_proj.upload(P.data(), P.size());
         }
 
+        if (t->k == 1 && t->p == 0)
+          build_k1_tables(h.get(), t);
         if (t->k == 2 && t->p == 1)
           build_k2_tables(h.get(), t);
         if (kw_supported(t->k, t->ndg))
           build_kw_tables(h.get(), t);
+        tm.lap("create: tables");
         launch_compute_cellJ(h.get());
+        tm.lap("create: cell Jacobians");
         colour_patches(h.get());
+        tm.lap("create: colouring");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         *out = h.release();
       });
@@ -400,6 +428,7 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
         if (!h || !facet_type)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs: null argument");
         (void)local_fct_id;  // implied by the patch maps (local id of the boundary facet in its only cell)
+        StageTimer tm;
         const size_t nf = h->nfct;
         // every boundary facet has to be classified for every RHS (se/Patch.cpp:464-470)
         h->d_facet_type.upload(facet_type, (size_t)h->nrhs * nf);
@@ -410,6 +439,7 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
         for (int r = 0; r < h->nrhs; ++r)
           if (bflux && bflux[r])
             CUDA_CHECK(cudaMemcpy(h->d_bflux.p + (size_t)r * nb, bflux[r], nb * sizeof(double), cudaMemcpyHostToDevice));
+        tm.lap("set_bcs: facet types + bflux");
         if (node_on_stress_bnd)
         {
           h->d_node_on_bnd.upload(node_on_stress_bnd, h->nnode);
@@ -464,16 +494,22 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
               h->h_group_off.push_back((int32_t)gorder.size());
             }
           }
-          colour_patches(h);
+          if (!gorder.empty() || h->h_order.empty() || h->coloured_with_groups)
+            colour_patches(h);
+          h->coloured_with_groups = !gorder.empty();
           std::copy(gorder.begin(), gorder.end(), h->h_order.begin());
         }
         else
         {
+          // the colouring of eqlb_create is still valid unless a previous BC set grouped patches
           h->h_grouped.assign(h->nnode, 0);
           h->h_group_off.clear();
-          colour_patches(h);
+          if (h->coloured_with_groups || h->h_order.empty())
+            colour_patches(h);
+          h->coloured_with_groups = false;
         }
 
+        tm.lap("set_bcs: grouping + colouring");
         // patch records (colour-sorted)
         h->pstride = ((size_t)h->nactive + 31) / 32 * 32;
         if (h->pstride == 0)
@@ -511,7 +547,9 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
           h->d_prec.zero(h->stream);
           h->d_seginfo.upload(seginfo.data(), seginfo.size());
         }
+        tm.lap("set_bcs: record buffers");
         launch_patch_builder(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        tm.lap("set_bcs: patch builder");
         h->bcs_set = true;
       });
 }

@@ -188,10 +188,12 @@ struct eqlb_handle
   std::vector<int32_t> h_colour_off;  // [ncolours+1]
   std::vector<int32_t> h_colour_maxnf; // [ncolours] max number of patch facets among those
   std::vector<int32_t> h_colour_fast; // [ncolours] number of leading patches of the colour eligible for the k=2 kernel
+  DevBuf<double> d_k1tab;             // gathered tables of the degree-1 kernel
   DevBuf<double> d_k2tab;             // gathered tables of the k=2 streaming kernel
   DevBuf<double> d_kwtab;             // gathered tables of the general warp-cooperative kernel
   std::vector<int32_t> h_colour;      // [nnode]
   int ncolours = 0;
+  bool coloured_with_groups = false;  // h_order currently starts with grouped boundary patches
   int nseg = 0;  // launch segments = spatial chunks x colours (h_colour_* arrays are per segment)
   size_t pstride = 0;
   DevBuf<int32_t> d_pnode, d_pcell;
@@ -234,6 +236,8 @@ void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF,
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma);
 void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* const* dout);
 void launch_korn(eqlb_handle* h, double* dKorn);
+void build_k1_tables(eqlb_handle* h, const eqlb_tables* t);
+void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff);
 void build_k2_tables(eqlb_handle* h, const eqlb_tables* t);
 bool kw_supported(int k, int ndg);
 void build_kw_tables(eqlb_handle* h, const eqlb_tables* t);

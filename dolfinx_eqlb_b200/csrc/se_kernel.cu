@@ -1325,8 +1325,9 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       int count = h->h_colour_off[c + 1] - first;
       static const bool stress_fast = getenv("EQLB_STRESS_GENERIC") == nullptr;
       const bool k2ok = (K == 2 && NDG == 3 && h->d_k2tab.p);
+      const bool k1ok = (K == 1 && NDG == 1 && h->d_k1tab.p);
       if (!(h->flags & EQLB_FLAG_GENERIC) && h->h_colour_maxnf[c] <= 16 && h->h_seg_lanes[c] > 0
-          && (stress ? (k2ok && stress_fast && !EV) : (k2ok || (kw_supported(K, NDG) && h->d_kwtab.p))))
+          && (stress ? (k2ok && stress_fast && !EV) : (k1ok || k2ok || (kw_supported(K, NDG) && h->d_kwtab.p))))
       {
         // specialised kernels for the eligible head of the segment, generic kernel for the rest
         static const bool force_kw = getenv("EQLB_KW") != nullptr;
@@ -1335,7 +1336,9 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
         // serialised on the stream); measured 14-25 % faster than load-add-store.
         static const int use_red = getenv("EQLB_RED") ? atoi(getenv("EQLB_RED")) : 1;
         const int nfast = h->h_colour_fast[c];
-        if (K == 2 && (!force_kw || stress))
+        if (K == 1)
+          launch_k1(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);
+        else if (K == 2 && (!force_kw || stress))
           launch_k2(h, EV, ptrs, first, nfast, use_red, h->h_colour_maxnf[c], h->h_seg_lanes[c], h->h_seg_recoff[c], stress);
         else
           launch_kw(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);

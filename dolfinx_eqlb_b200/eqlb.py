@@ -12,6 +12,7 @@ pointers).  All numerics run in the CUDA library behind the C ABI
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -109,7 +110,10 @@ class _Problem:
         flags = (1 if stress else 0) | (2 if atomic else 0) | (16 if host_pipeline else 0)
         self.stress = stress
         h = C.c_void_p()
+        t0 = time.perf_counter()
         _check(self.lib, self.lib.eqlb_create(C.byref(self._pm.struct), C.byref(self._pt.struct), nrhs, flags, C.byref(h)))
+        self.create_seconds = time.perf_counter() - t0  # mesh upload, Jacobians (C ABI call only)
+        self.set_bcs_seconds = 0.0
         self.h = h
 
     def __del__(self):
@@ -125,6 +129,7 @@ class _Problem:
 
     def set_bcs(self, bd: BoundaryData):
         nob = bd.node_on_stress_bnd
+        t0 = time.perf_counter()
         _check(
             self.lib,
             self.lib.eqlb_set_bcs(
@@ -135,6 +140,7 @@ class _Problem:
                 nob.ctypes.data_as(cabi.c_int8_p) if nob is not None else cabi.c_int8_p(),
             ),
         )
+        self.set_bcs_seconds = time.perf_counter() - t0  # colouring, device patch builder (C ABI call only)
 
     def launch_count(self):
         return int(self.lib.eqlb_launch_count(self.h))

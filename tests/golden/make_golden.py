@@ -27,6 +27,25 @@ CASES = [
 ]
 
 
+# elasticity rows with weak symmetry + Korn constants: name, kind, n, scramble, perturb, k, traction sides, seed
+# (traction layouts of test_stressqlb_bcond.py:167-190; [1, 2] needs the grouped corner patches)
+STRESS_CASES = [
+    ("stress_k2_crossed5_scr", "crossed", 5, 3, 0.2, 2, [1], 6),
+    ("stress_k2_crossed4_corner", "crossed", 4, None, 0.2, 2, [1, 2], 7),
+    ("stress_k3_crossed3", "crossed", 3, 5, 0.1, 3, [1], 8),
+]
+
+
+def build_stress(name, kind, n, scramble, perturb, k, nsides, seed):
+    from test_gpu_stress import elasticity_case
+    from dolfinx_eqlb_b200 import eqlb
+
+    m = make_mesh(kind, n, scramble, perturb)
+    T, G, f, bfp, bcs, neu = elasticity_case(m, k, nsides, seed=seed)
+    bd = eqlb.boundarydata(bcs, m, T, bfp, True)
+    return m, T, G, f, bfp, bcs, bd
+
+
 def build(name, path, kind, n, scramble, perturb, k, nsets, seed):
     m = make_mesh(kind, n, scramble, perturb)
     case = PoissonCase(m, k, nsets, seed=seed, hom=(path == "ev"))
@@ -57,6 +76,18 @@ def main():
             reversed=maps["reversed"], cell_node=m.cell_node, x=m.x,
         )
         print("wrote", name)
+    for spec in STRESS_CASES:
+        m, T, G, f, bfp, bcs, bd = build_stress(*spec)
+        bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
+        sig, korn = po.se_run(m, T, bc, G, f, stress=True, korn=True)
+        for r in range(2):
+            assert fm.check_divergence(m, T, sig[r], G[r], f[r]) < 1e-12
+            assert fm.check_jump(m, T, sig[r], G[r]) < 1e-10
+        ws = fm.check_weak_symmetry(m, T, sig[0], sig[1])
+        assert ws < 1e-10, (spec[0], ws)
+        np.savez_compressed(os.path.join(out, spec[0] + ".npz"), G=np.array(G), F=np.array(f), sigma=np.array(sig), korn=korn,
+                            cell_node=m.cell_node, x=m.x)
+        print("wrote", spec[0])
 
 
 if __name__ == "__main__":

@@ -158,6 +158,8 @@ def load_library():
     lib.eqlb_get_ev_dofmaps.argtypes = [H, c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                         c_int32_p]
     lib.eqlb_get_ev_dofmaps.restype = C.c_int
+    lib.eqlb_set_part.argtypes = [H, C.c_int]
+    lib.eqlb_set_part.restype = C.c_int
     lib.eqlb_launch_count.argtypes = [H]
     lib.eqlb_launch_count.restype = C.c_int64
     lib.eqlb_last_error.restype = C.c_char_p

@@ -112,11 +112,29 @@ void colour_patches(eqlb_handle* h)
     if (h->ncell < 4096)
       nchunk = 1;
   }
+  // distributed runs: interface patches (a cell of the patch holds a vertex of another rank)
+  // first, so that their halo exchange can overlap the interior patches (eqlb_set_part)
+  h->interface_first = false;
+  if ((h->flags & EQLB_FLAG_INTERFACE_FIRST) && !(h->flags & EQLB_FLAG_HOST_PIPELINE) && h->nactive < h->nnode)
+  {
+    h->interface_first = true;
+    nchunk = 2;
+  }
   h->nchunk = nchunk;
   // stage of a patch = chunk of its LAST cell: all its inputs are on the device once the
   // cell slabs 0..stage have arrived
   auto chunk_of = [&](int z)
   {
+    if (h->interface_first)
+    {
+      for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
+      {
+        const int32_t* cn = &h->h_cell_node[3 * (size_t)h->h_node_cell[i]];
+        if (!h->h_owned[cn[0]] || !h->h_owned[cn[1]] || !h->h_owned[cn[2]])
+          return 0;
+      }
+      return 1;
+    }
     int32_t cmax = 0;
     for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
       cmax = std::max(cmax, h->h_node_cell[i]);
@@ -159,7 +177,7 @@ void colour_patches(eqlb_handle* h)
   // last stage with a patch that adds into it
   h->h_se_slabs.clear();
   h->h_ev_slabs.clear();
-  if (nchunk > 1)
+  if (nchunk > 1 && !h->interface_first)
   {
     std::vector<int> nstage(n, -1);
     for (int z = 0; z < n; ++z)
@@ -705,6 +723,24 @@ int eqlb_get_ev_dofmaps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t
       });
 }
 
+int eqlb_set_part(eqlb_handle* h, int part)
+{
+  return guarded(
+      [&]
+      {
+        if (!h)
+          throw EqlbError(EQLB_ERR_INPUT, "null handle");
+        if (part != EQLB_PART_ALL && part != EQLB_PART_INTERFACE && part != EQLB_PART_INTERIOR)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_part: unknown part");
+        if (part != EQLB_PART_ALL && (!h->interface_first || (h->flags & EQLB_FLAG_ATOMIC) || !h->h_group_off.empty()))
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_set_part: handle was not created with EQLB_FLAG_INTERFACE_FIRST on a "
+                                          "partitioned mesh (or uses atomics / grouped patches)");
+        h->part = part;
+        h->win_lo = (part == EQLB_PART_INTERIOR) ? h->ncolours : 0;
+        h->win_hi = (part == EQLB_PART_INTERFACE) ? h->ncolours : (1 << 30);
+      });
+}
+
 // Common driver of eqlb_se_run / eqlb_ev_run: device pointers are used in place; host
 // pointers are staged, either in one piece or - with EQLB_FLAG_HOST_PIPELINE - stage by
 // stage on three streams so that both PCIe directions and the SMs work at the same time.
@@ -763,7 +799,7 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
     dK = h->d_stage_korn.p;
   }
   // (grouped boundary patches of the stress path read the accumulated global stress: not staged)
-  const bool pipelined = h->nchunk > 1 && !(h->flags & EQLB_FLAG_ATOMIC) && h->h_group_off.empty()
+  const bool pipelined = h->nchunk > 1 && !h->interface_first && !(h->flags & EQLB_FLAG_ATOMIC) && h->h_group_off.empty()
                          && !korn && h->nseg == h->nchunk * h->ncolours;
   if (!pipelined)
   {

@@ -206,6 +206,8 @@ struct eqlb_handle
 
   // host pipeline (EQLB_FLAG_HOST_PIPELINE): spatial stages = chunks of the cell range
   int nchunk = 1;
+  bool interface_first = false;  // chunk 0 = interface patches of a distributed run, chunk 1 = interior
+  int part = EQLB_PART_ALL;
   int win_lo = 0, win_hi = 1 << 30;  // window of launch segments executed by launch_se / launch_ev
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;

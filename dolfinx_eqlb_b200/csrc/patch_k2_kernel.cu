@@ -591,14 +591,15 @@ __device__ __forceinline__ double seg_sum(double v)
 }
 
 // shared-memory scratch of the weak-symmetry stage per patch (doubles): factor [4][S],
-// X [2][S+1][S+1]; padded to 8 mod 16 so that the patches of a warp use different banks
+// X [2][S+1][S+1]; tile stride = S mod 16 so that the 32/S patches of a warp spread over
+// the banks (ncu: 17.9 M bank conflicts per S=4 launch with a stride of 8 mod 16)
 template <int S>
 struct K2Stress
 {
   static constexpr int XROW = S + 1;
   static constexpr int O_X = 4 * S;
   static constexpr int RAW = O_X + 2 * (S + 1) * XROW;
-  static constexpr int TILE = RAW + ((8 - RAW % 16) + 16) % 16;
+  static constexpr int TILE = RAW + ((S - RAW % 16) + 32) % 16;
 };
 
 template <bool EV, int S, int MINB, bool STRESS>

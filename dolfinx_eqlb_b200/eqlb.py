@@ -102,12 +102,13 @@ class _Problem:
     """Owns the device-resident problem (C-ABI handle)."""
 
     def __init__(self, mesh: Mesh, tables: Tables, nrhs: int, stress=False, atomic=False, node_owned=None,
-                 host_pipeline=False, generic=False):
+                 host_pipeline=False, generic=False, interface_first=False):
         self.lib = cabi.load_library()
         self.mesh, self.tables, self.nrhs = mesh, tables, nrhs
         self._pm = cabi.PackedMesh(mesh, tables.ndg, node_owned)
         self._pt = cabi.PackedTables(tables)
-        flags = (1 if stress else 0) | (2 if atomic else 0) | (4 if generic else 0) | (16 if host_pipeline else 0)
+        flags = ((1 if stress else 0) | (2 if atomic else 0) | (4 if generic else 0) | (16 if host_pipeline else 0)
+                 | (32 if interface_first else 0))
         self.stress = stress
         h = C.c_void_p()
         t0 = time.perf_counter()
@@ -123,6 +124,10 @@ class _Problem:
                 self.h = None
         except Exception:
             pass
+
+    def set_part(self, part: int):
+        """0: all patches, 1: interface patches of a partitioned mesh, 2: interior patches (`eqlb_set_part`)."""
+        _check(self.lib, self.lib.eqlb_set_part(self.h, int(part)))
 
     def set_stream(self, stream_ptr):
         _check(self.lib, self.lib.eqlb_set_stream(self.h, C.c_void_p(stream_ptr)))
@@ -267,7 +272,7 @@ class FluxEqlbSE(FluxEquilibrator):
 
     def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, equilibrate_stress=False,
                  estimate_korn_constant=False, degree_proj=None, atomic=False, node_owned=None, host_pipeline=True,
-                 generic=False):
+                 generic=False, interface_first=False):
         super().__init__(degree_flux, len(list_rhs), equilibrate_stress)
         if len(list_proj_flux) != self.n_fluxes:
             raise RuntimeError("Mismatching inputs!")
@@ -276,7 +281,8 @@ class FluxEqlbSE(FluxEquilibrator):
         self.list_rhs, self.list_proj_flux = list_rhs, list_proj_flux
         self.estimate_korn_constant = estimate_korn_constant
         self.korn_constants = np.zeros(msh.ncell) if estimate_korn_constant else None
-        self.problem = _Problem(msh, self.tables, self.n_fluxes, equilibrate_stress, atomic, node_owned, host_pipeline, generic)
+        self.problem = _Problem(msh, self.tables, self.n_fluxes, equilibrate_stress, atomic, node_owned, host_pipeline, generic,
+                                interface_first)
         self.list_flux = [np.zeros(msh.ncell * self.tables.nrt) for _ in range(self.n_fluxes)]
         self._fresh = True  # list_flux still holds the zeros it was created with
 
@@ -304,14 +310,15 @@ class FluxEqlbEV(FluxEquilibrator):
     """`eqlb/FluxEqlbEV.py:20-188` on top of the CUDA hot path; the flux lives in
     the conforming hierarchic RT_k space ([facet dofs nfct*k][cell dofs])."""
 
-    def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, node_owned=None, host_pipeline=True, generic=False):
+    def __init__(self, degree_flux, msh: Mesh, list_rhs, list_proj_flux, node_owned=None, host_pipeline=True, generic=False,
+                 interface_first=False):
         super().__init__(degree_flux, len(list_rhs), False)
         if len(list_proj_flux) != self.n_fluxes:
             raise RuntimeError("Missmatching inputs!")
         self.mesh = msh
         self.tables = make_tables(degree_flux)
         self.list_rhs, self.list_proj_flux = list_rhs, list_proj_flux
-        self.problem = _Problem(msh, self.tables, self.n_fluxes, False, False, node_owned, host_pipeline, generic)
+        self.problem = _Problem(msh, self.tables, self.n_fluxes, False, False, node_owned, host_pipeline, generic, interface_first)
         k = degree_flux
         self.ndofs = msh.nfct * k + msh.ncell * (k * k - k)
         self.list_flux = [np.zeros(self.ndofs) for _ in range(self.n_fluxes)]

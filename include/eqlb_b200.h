@@ -54,6 +54,10 @@ extern "C" {
  * stage s+1, patch kernels of stage s and device->host copy of finished DOF ranges overlap on
  * three streams (PCIe both directions busy); costs a few extra launches on device-pointer calls */
 #define EQLB_FLAG_HOST_PIPELINE 16u
+/* distributed runs (node_owned given): patches that touch a cell shared with another rank are
+ * ordered first, so that eqlb_set_part can launch them separately and the halo exchange of
+ * their DOFs overlaps the interior patches (ignored together with EQLB_FLAG_HOST_PIPELINE) */
+#define EQLB_FLAG_INTERFACE_FIRST 32u
 
 /* wire values, `base/Patch.hpp:20-33` */
 enum eqlb_patch_type { EQLB_PATCH_INTERNAL = 0, EQLB_PATCH_ESSNT_DUAL = 1,
@@ -170,6 +174,17 @@ int eqlb_get_se_dofmaps(eqlb_handle* h, int32_t* dofmap, int32_t* projflux_fct,
 int eqlb_get_ev_dofmaps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t* fcts, int8_t* inodes_local,
                         int32_t* dofs_elmt, int32_t* dofs_patch, int32_t* dofs_global,
                         int32_t* list_patch, int32_t* list_global);
+
+/* Which patches the next eqlb_se_run / eqlb_ev_run calls launch: EQLB_PART_ALL (default),
+ * EQLB_PART_INTERFACE (owned patches touching a cell that holds a vertex of another rank) or
+ * EQLB_PART_INTERIOR (the rest).  Needs EQLB_FLAG_INTERFACE_FIRST.  Interior patches never
+ * write a DOF the halo exchange reads or updates, so
+ *   run(INTERFACE); record event; run(INTERIOR) || [wait event; halo sum on a second stream]
+ * gives the result of run(ALL); halo sum with the exchange hidden behind the interior kernels. */
+#define EQLB_PART_ALL 0
+#define EQLB_PART_INTERFACE 1
+#define EQLB_PART_INTERIOR 2
+int eqlb_set_part(eqlb_handle* h, int part);
 
 /* number of kernel launches issued by this handle so far (bench "gpu_launches") */
 int64_t eqlb_launch_count(eqlb_handle* h);

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, path, k, out):
+def _worker(rank, world, port, path, k, out, split=False):
     import torch.distributed as dist
 
     from common import make_mesh
@@ -40,9 +40,17 @@ def _worker(rank, world, port, path, k, out):
     Gl = G.reshape(m.ncell, -1)[part.cell_gid].ravel()
     Fl = F.reshape(m.ncell, -1)[part.cell_gid].ravel()
     cls = eqlb.FluxEqlbSE if path == "se" else eqlb.FluxEqlbEV
-    eq = cls(k, lm, [Fl], [Gl], node_owned=part.node_owned)
+    eq = cls(k, lm, [Fl], [Gl], node_owned=part.node_owned, host_pipeline=not split, interface_first=split)
     eq.set_boundary_conditions([lm.bfct[lm.bfct_side > 0].astype(np.int32)], [[]])
-    eq.equilibrate_fluxes()
+    if split:
+        # interface patches and interior patches in two calls (eqlb_set_part): same total
+        eq.problem.set_part(1)
+        eq.equilibrate_fluxes()
+        eq.problem.set_part(2)
+        eq.equilibrate_fluxes()
+        eq.problem.set_part(0)
+    else:
+        eq.equilibrate_fluxes()
     loc, gid = dd.se_dof_gids(part, T.nrt) if path == "se" else dd.ev_dof_gids(part, k, m.nnode)
     x = torch.from_numpy(eq.list_flux[0]).cuda()
     dd.HaloExchange(loc, gid, device="cuda").apply([x])
@@ -62,15 +70,44 @@ def _worker(rank, world, port, path, k, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("path,k", [("se", 2), ("ev", 2), ("se", 3)])
-def test_two_gpu_halo_sum(path, k):
+@pytest.mark.parametrize("path,k,split", [("se", 2, False), ("ev", 2, False), ("se", 3, False), ("ev", 2, True), ("se", 1, True)])
+def test_two_gpu_halo_sum(path, k, split):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(2, port, path, k, out), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, port, path, k, out, split), nprocs=2, join=True)
         res = dict(out)
     assert len(res) == 2
     for e in res.values():
         assert e < 1e-12
+
+
+def test_set_part_single_gpu():
+    """eqlb_set_part on one GPU with an artificial ownership mask: interface + interior
+    patches in two calls give the one-call result; the interior part leaves the DOFs of
+    cells with a foreign vertex untouched."""
+    from common import PoissonCase, make_mesh
+    from dolfinx_eqlb_b200 import eqlb
+
+    m = make_mesh("crossed", 10, 2, perturb=0.2)
+    case = PoissonCase(m, 2, [[]], seed=4, galerkin=False)
+    owned = (m.x[:, 1] < 0.55).astype(np.uint8)
+    bf = [m.boundary_facets([1, 2, 3, 4])]
+    whole = eqlb.FluxEqlbSE(2, m, case.F, case.G, node_owned=owned, host_pipeline=False)
+    whole.set_boundary_conditions(bf, [[]])
+    whole.equilibrate_fluxes()
+    eq = eqlb.FluxEqlbSE(2, m, case.F, case.G, node_owned=owned, host_pipeline=False, interface_first=True)
+    eq.set_boundary_conditions(bf, [[]])
+    eq.problem.set_part(2)
+    eq.equilibrate_fluxes()
+    nrt = case.T.nrt
+    shared_cells = (owned[m.cell_node] == 0).any(axis=1)
+    assert np.abs(eq.list_flux[0].reshape(m.ncell, nrt)[shared_cells]).max() == 0.0
+    eq.problem.set_part(1)
+    eq.equilibrate_fluxes()
+    assert np.abs(eq.list_flux[0] - whole.list_flux[0]).max() < 1e-13 * np.abs(whole.list_flux[0]).max()
+    # a handle without the flag refuses
+    with pytest.raises(RuntimeError):
+        whole.problem.set_part(1)

@@ -68,6 +68,15 @@ struct StageTimer
 
 void colour_patches(eqlb_handle* h)
 {
+  // topology arrays: the caller's (during eqlb_create) or the handle's copies (stress handles,
+  // which may have to recolour when a BC set groups boundary patches)
+  const eqlb_handle::HostTopo& T = h->topo;
+  if (!T.node_cell_off)
+  {
+    if (h->nactive == 0 && h->nseg > 0)
+      return;  // nothing owned: the (empty) colouring of eqlb_create stands
+    throw EqlbError(EQLB_ERR_STATE, "colouring: host topology not available");
+  }
   const int n = h->nnode;
   h->h_colour.assign(n, -1);
   int ncol = 0;
@@ -77,9 +86,9 @@ void colour_patches(eqlb_handle* h)
     if (!h->h_owned[z] || h->h_grouped[z])
       continue;
     uint64_t used = 0;
-    for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
+    for (int i = T.node_cell_off[z]; i < T.node_cell_off[z + 1]; ++i)
     {
-      const int32_t* cn = &h->h_cell_node[3 * (size_t)h->h_node_cell[i]];
+      const int32_t* cn = &T.cell_node[3 * (size_t)T.node_cell[i]];
       for (int j = 0; j < 3; ++j)
       {
         const int c = h->h_colour[cn[j]];
@@ -127,17 +136,17 @@ void colour_patches(eqlb_handle* h)
   {
     if (h->interface_first)
     {
-      for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
+      for (int i = T.node_cell_off[z]; i < T.node_cell_off[z + 1]; ++i)
       {
-        const int32_t* cn = &h->h_cell_node[3 * (size_t)h->h_node_cell[i]];
+        const int32_t* cn = &T.cell_node[3 * (size_t)T.node_cell[i]];
         if (!h->h_owned[cn[0]] || !h->h_owned[cn[1]] || !h->h_owned[cn[2]])
           return 0;
       }
       return 1;
     }
     int32_t cmax = 0;
-    for (int i = h->h_node_cell_off[z]; i < h->h_node_cell_off[z + 1]; ++i)
-      cmax = std::max(cmax, h->h_node_cell[i]);
+    for (int i = T.node_cell_off[z]; i < T.node_cell_off[z + 1]; ++i)
+      cmax = std::max(cmax, T.node_cell[i]);
     return (int)((long)cmax * nchunk / std::max(h->ncell, 1));
   };
   h->nseg = nchunk * ncol;
@@ -156,7 +165,7 @@ void colour_patches(eqlb_handle* h)
   auto eligible = [&](int z)
   {
     return h->nrhs == 1
-           || (h->h_node_fct_off[z + 1] - h->h_node_fct_off[z]) == (h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]);
+           || (T.node_fct_off[z + 1] - T.node_fct_off[z]) == (T.node_cell_off[z + 1] - T.node_cell_off[z]);
   };
   h->h_colour_fast.assign(h->nseg, 0);
   h->h_colour_maxnf.assign(h->nseg, 0);
@@ -169,7 +178,7 @@ void colour_patches(eqlb_handle* h)
         if (pass == 0)
         {
           h->h_colour_fast[sg]++;
-          h->h_colour_maxnf[sg] = std::max(h->h_colour_maxnf[sg], h->h_node_fct_off[z + 1] - h->h_node_fct_off[z]);
+          h->h_colour_maxnf[sg] = std::max(h->h_colour_maxnf[sg], T.node_fct_off[z + 1] - T.node_fct_off[z]);
         }
       }
 
@@ -192,14 +201,14 @@ void colour_patches(eqlb_handle* h)
       int fin = 0;
       for (size_t c = c0; c < c1; ++c)
         for (int j = 0; j < 3; ++j)
-          fin = std::max(fin, nstage[h->h_cell_node[3 * c + j]]);
+          fin = std::max(fin, nstage[T.cell_node[3 * c + j]]);
       h->h_se_slabs.push_back({c0 * h->nrt, (c1 - c0) * h->nrt, fin});
       if (ncd)
         h->h_ev_slabs.push_back({(size_t)h->nfct * kk + c0 * ncd, (c1 - c0) * ncd, fin});
       const size_t f0 = slab_lo(h->nfct, sidx), f1 = slab_lo(h->nfct, sidx + 1);
       int ffin = 0;
       for (size_t f = f0; f < f1; ++f)
-        ffin = std::max(ffin, std::max(nstage[h->h_fct_node[2 * f]], nstage[h->h_fct_node[2 * f + 1]]));
+        ffin = std::max(ffin, std::max(nstage[T.fct_node[2 * f]], nstage[T.fct_node[2 * f + 1]]));
       h->h_ev_slabs.push_back({f0 * kk, (f1 - f0) * kk, ffin});
     }
   }
@@ -308,12 +317,20 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
         h->d_fct_perms.upload(mesh->fct_perms, nc * 3);
         tm.lap("create: mesh upload");
-        h->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
-        h->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
-        h->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
-        h->h_node_fct_off.assign(mesh->node_fct_off, mesh->node_fct_off + nn + 1);
-        h->h_node_fct.assign(mesh->node_fct, mesh->node_fct + mesh->node_fct_off[nn]);
-        h->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
+        // host topology: colouring reads the caller's arrays; only stress handles keep copies
+        // (boundary-patch grouping and recolouring in eqlb_set_bcs)
+        h->topo = {mesh->node_cell_off, mesh->node_cell, mesh->cell_node, mesh->node_fct_off, mesh->node_fct, mesh->fct_node};
+        if (flags & EQLB_FLAG_STRESS)
+        {
+          h->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
+          h->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
+          h->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
+          h->h_node_fct_off.assign(mesh->node_fct_off, mesh->node_fct_off + nn + 1);
+          h->h_node_fct.assign(mesh->node_fct, mesh->node_fct + mesh->node_fct_off[nn]);
+          h->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
+          h->topo = {h->h_node_cell_off.data(), h->h_node_cell.data(), h->h_cell_node.data(),
+                     h->h_node_fct_off.data(), h->h_node_fct.data(), h->h_fct_node.data()};
+        }
         h->h_grouped.assign(nn, 0);
 
         tm.lap("create: host copies");
@@ -417,6 +434,8 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         launch_compute_cellJ(h.get());
         tm.lap("create: cell Jacobians");
         colour_patches(h.get());
+        if (!(flags & EQLB_FLAG_STRESS))
+          h->topo = {};  // the caller's arrays are not referenced after eqlb_create
         tm.lap("create: colouring");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         *out = h.release();

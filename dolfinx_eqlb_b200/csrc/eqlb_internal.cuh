@@ -166,7 +166,13 @@ struct eqlb_handle
   DevBuf<uint8_t> d_fct_perms;
   DevBuf<double> d_cellJ;  // [ncell][4] Jacobians (J00,J01,J10,J11)
 
-  // host copies needed for colouring / validation
+  // host topology used by the colouring (see eqlb_create)
+  struct HostTopo
+  {
+    const int32_t *node_cell_off = nullptr, *node_cell = nullptr, *cell_node = nullptr, *node_fct_off = nullptr,
+                  *node_fct = nullptr, *fct_node = nullptr;
+  } topo;
+  // host copies needed for grouping / recolouring (stress handles only)
   std::vector<int32_t> h_node_cell_off, h_node_cell, h_cell_node, h_node_fct_off, h_node_fct, h_fct_node;
   std::vector<uint8_t> h_grouped;      // node is member of a grouped boundary patch set
   std::vector<int32_t> h_group_off;    // offsets of the groups in h_order (first member = inner patch)

@@ -189,7 +189,7 @@ def workload_config(args):
         "workload": f"{name}, degree_flux={args.k}, {args.n}x{args.n} crossed unit square, pure Dirichlet, nrhs={args.nrhs}",
         "path": args.path, "degree_flux": args.k, "n": args.n, "nrhs": args.nrhs,
         "l2": "inputs larger than L2 (no flush needed)", "accumulation": "colour-ordered (deterministic)",
-        "parallelism": "vertex strips, owner-computes patches, NCCL halo sum" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "single GPU",
+        "parallelism": "vertex strips, owner-computes patches, halo sum over NVLink peer memory" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "single GPU",
     }
 
 
@@ -277,7 +277,11 @@ def main():
             loc, gid = dd.se_dof_gids(part, T.nrt)
         else:
             loc, gid = dd.ev_dof_gids(part, k, nnode_global)
-        hx = dd.HaloExchange(loc, gid, device="cuda")
+        # halo sum: one kernel per rank over NVLink peer memory (EQLB_HALO=nccl: NCCL send/recv + index_add)
+        if os.environ.get("EQLB_HALO", "p2p") == "nccl":
+            hx = dd.HaloExchange(loc, gid, device="cuda")
+        else:
+            hx = dd.P2PHaloExchange(loc, gid, nrhs_max=nrhs)
 
     def run_device():
         if args.path == "se":

@@ -160,6 +160,16 @@ def load_library():
     lib.eqlb_get_ev_dofmaps.restype = C.c_int
     lib.eqlb_set_part.argtypes = [H, C.c_int]
     lib.eqlb_set_part.restype = C.c_int
+    c_int64_p = C.POINTER(C.c_int64)
+    c_ubyte_p = C.POINTER(C.c_ubyte)
+    lib.eqlb_halo_create.argtypes = [C.c_int, c_int64_p, C.POINTER(c_int64_p), C.c_int, C.POINTER(H), c_ubyte_p, c_int64_p]
+    lib.eqlb_halo_create.restype = C.c_int
+    lib.eqlb_halo_connect.argtypes = [H, C.c_int, c_ubyte_p, C.c_int64, C.c_int]
+    lib.eqlb_halo_connect.restype = C.c_int
+    lib.eqlb_halo_apply.argtypes = [H, C.POINTER(c_double_p), C.c_int, C.c_void_p]
+    lib.eqlb_halo_apply.restype = C.c_int
+    lib.eqlb_halo_destroy.argtypes = [H]
+    lib.eqlb_halo_destroy.restype = None
     lib.eqlb_launch_count.argtypes = [H]
     lib.eqlb_launch_count.restype = C.c_int64
     lib.eqlb_last_error.restype = C.c_char_p

@@ -5,9 +5,10 @@ The reference has no working distributed path (`FluxEqlbSE.py:164` TODO; loops r
 SURVEY 5).  Here the mesh is partitioned by vertices; a rank holds all cells of its owned
 vertices (owned cells + one layer of halo cells), equilibrates the patches of its owned
 vertices only (`eqlb_mesh.node_owned`) and afterwards the partial sums on DOFs that also
-live on other ranks are exchanged point-to-point (`torch.distributed` send/recv: NCCL over
-NVLink on GPUs, gloo on CPU for the tests) and added in ascending rank order, which makes
-the result independent of message arrival order.
+live on other ranks are exchanged point-to-point and added in ascending rank order, which
+makes the result independent of message arrival order: `P2PHaloExchange` (GPUs: one kernel
+per rank over NVLink peer memory, `csrc/halo_p2p.cu`) or `HaloExchange` (`torch.distributed`
+send/recv: NCCL on GPUs, gloo on CPU for the tests); both give the same bits.
 
 Patches never talk to each other, so this is the only exchange step of the path; message
 size is O(interface cells x ndofs x 8 B) (about 1 MB for a 1024-wide strip), i.e. latency
@@ -179,3 +180,72 @@ class HaloExchange:
         for (q, idx), recv in zip(self.neigh, recvs):  # ascending rank order: deterministic
             for i, x in enumerate(xs):
                 x.index_add_(0, idx, recv[i])
+
+
+class P2PHaloExchange:
+    """Same contract as `HaloExchange` on CUDA tensors, but the data path is one kernel per
+    rank over NVLink peer memory (`csrc/halo_p2p.cu`): pack -> flag in the neighbour's memory
+    -> add the neighbours' values, neighbours in ascending rank order (deterministic, the
+    same bits as `HaloExchange`).  `torch.distributed` is only used once, to exchange the CUDA
+    IPC handles of the communication buffers."""
+
+    def __init__(self, loc_idx, gid, nrhs_max=1, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import cabi
+
+        self.torch, self.C, self.cabi = torch, C, cabi
+        self.lib = cabi.load_library()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        order = np.argsort(gid, kind="stable")
+        gid_sorted, loc_sorted = gid[order], loc_idx[order]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, gid_sorted, group=group)
+        self.neigh = []
+        for q in range(world):
+            if q == rank:
+                continue
+            common, ia, _ = np.intersect1d(gid_sorted, gathered[q], assume_unique=True, return_indices=True)
+            if common.size:
+                self.neigh.append((q, np.ascontiguousarray(loc_sorted[ia], dtype=np.int64)))
+        nn = len(self.neigh)
+        counts = (C.c_int64 * max(nn, 1))(*[idx.size for _, idx in self.neigh])
+        c_int64_p = C.POINTER(C.c_int64)
+        idxp = (c_int64_p * max(nn, 1))(*[idx.ctypes.data_as(c_int64_p) for _, idx in self.neigh])
+        handle = (C.c_ubyte * 64)()
+        send_off = (C.c_int64 * max(nn, 1))()
+        self.h = C.c_void_p()
+        rc = self.lib.eqlb_halo_create(nn, counts, idxp, int(nrhs_max), C.byref(self.h), handle, send_off)
+        if rc != 0:
+            raise RuntimeError(self.lib.eqlb_last_error().decode())
+        mine = {"handle": bytes(handle), "neigh": [q for q, _ in self.neigh], "send_off": [int(v) for v in send_off[:nn]]}
+        infos = [None] * world
+        dist.all_gather_object(infos, mine, group=group)
+        for n, (q, _) in enumerate(self.neigh):
+            peer = infos[q]
+            slot = peer["neigh"].index(rank)
+            ph = (C.c_ubyte * 64).from_buffer_copy(peer["handle"])
+            rc = self.lib.eqlb_halo_connect(self.h, n, ph, peer["send_off"][slot], slot)
+            if rc != 0:
+                raise RuntimeError(self.lib.eqlb_last_error().decode())
+        self.bytes_per_apply = sum(int(idx.size) * 8 for _, idx in self.neigh)
+        dist.barrier(group=group)
+
+    def apply(self, xs):
+        """xs: list of 1-D float64 CUDA tensors (one per RHS), updated in place on the current stream."""
+        C, cabi = self.C, self.cabi
+        arr = (cabi.c_double_p * len(xs))(*[C.cast(x.data_ptr(), cabi.c_double_p) for x in xs])
+        rc = self.lib.eqlb_halo_apply(self.h, arr, len(xs), C.c_void_p(self.torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(self.lib.eqlb_last_error().decode())
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.eqlb_halo_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -186,6 +186,25 @@ int eqlb_get_ev_dofmaps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t
 #define EQLB_PART_INTERIOR 2
 int eqlb_set_part(eqlb_handle* h, int part);
 
+/* ---- multi-GPU halo sum over NVLink peer memory (one process per GPU, no NCCL on the data path) ----
+ * The reference sums shared DOFs through PETSc ghost updates after `equilibrate_fluxes`
+ * (`x.scatter_reverse`); here every rank packs its shared values, publishes them with a flag
+ * in the neighbour's memory and adds the neighbours' values, all in ONE kernel launch
+ * (csrc/halo_p2p.cu).  Neighbours are given in ascending rank order; `idx[n]` are the local
+ * DOF indices shared with neighbour n, ordered identically (by global id) on both sides.
+ *   eqlb_halo_create  -> CUDA IPC handle of the own buffer + byte offsets of the send areas;
+ *   the caller exchanges (handle, offsets) between the ranks (e.g. all_gather) and calls
+ *   eqlb_halo_connect(h, n, neighbour's handle, neighbour's offset of the area for this rank,
+ *                     this rank's position in the neighbour's neighbour list);
+ *   eqlb_halo_apply(h, x, nrhs, stream): x[r][idx] += sum over neighbours, deterministic. */
+typedef struct eqlb_halo eqlb_halo;
+int eqlb_halo_create(int nneigh, const int64_t* counts, const int64_t* const* idx, int nrhs_max,
+                     eqlb_halo** out, unsigned char* ipc_handle_out, int64_t* send_off_out);
+int eqlb_halo_connect(eqlb_halo* h, int n, const unsigned char* peer_ipc_handle,
+                      int64_t peer_send_off, int peer_slot);
+int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream);
+void eqlb_halo_destroy(eqlb_halo* h);
+
 /* number of kernel launches issued by this handle so far (bench "gpu_launches") */
 int64_t eqlb_launch_count(eqlb_handle* h);
 

@@ -53,7 +53,19 @@ def _worker(rank, world, port, path, k, out, split=False):
         eq.equilibrate_fluxes()
     loc, gid = dd.se_dof_gids(part, T.nrt) if path == "se" else dd.ev_dof_gids(part, k, m.nnode)
     x = torch.from_numpy(eq.list_flux[0]).cuda()
-    dd.HaloExchange(loc, gid, device="cuda").apply([x])
+    # halo sum over NVLink peer memory (one kernel per rank) == NCCL send/recv + index_add, bit
+    # for bit, also when repeated (flag epochs, double buffering)
+    y = [x.clone(), (0.5 * x).clone()]
+    z = [t.clone() for t in y]
+    nccl, p2p = dd.HaloExchange(loc, gid, device="cuda"), dd.P2PHaloExchange(loc, gid, nrhs_max=2)
+    for _ in range(5):
+        nccl.apply(y)
+        p2p.apply(z)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(y, z))
+    dist.barrier()
+    p2p.apply([x])
+    torch.cuda.synchronize()
     # single-GPU reference of the whole mesh on this rank's device
     ref_eq = cls(k, m, [F], [G])
     ref_eq.set_boundary_conditions([m.boundary_facets([1, 2, 3, 4])], [[]])

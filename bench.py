@@ -281,7 +281,12 @@ def main():
         if os.environ.get("EQLB_HALO", "p2p") == "nccl":
             hx = dd.HaloExchange(loc, gid, device="cuda")
         else:
-            hx = dd.P2PHaloExchange(loc, gid, nrhs_max=nrhs)
+            try:
+                hx = dd.P2PHaloExchange(loc, gid, nrhs_max=nrhs)
+            except RuntimeError as e:  # e.g. CUDA IPC not permitted on this box: all ranks raise together
+                if rank == 0:
+                    print(f"[bench] peer-memory halo unavailable ({e}); using NCCL send/recv", file=sys.stderr)
+                hx = dd.HaloExchange(loc, gid, device="cuda")
 
     def run_device():
         if args.path == "se":
@@ -423,10 +428,13 @@ def main():
         v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress)
         cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": "port",
                "sample": f"{procs} processes x crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches each) of the same workload, mean of 3 steps"}
+    cfg = workload_config(args)
+    if hx is not None:
+        cfg["halo"] = type(hx).__name__
     line = {
         "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+        "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
         "e2e": {"value": npatch_total / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         # one-time cost per (mesh, BC set), outside the timed region: the reference redoes this work in every call

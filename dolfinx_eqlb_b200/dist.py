@@ -218,19 +218,27 @@ class P2PHaloExchange:
         handle = (C.c_ubyte * 64)()
         send_off = (C.c_int64 * max(nn, 1))()
         self.h = C.c_void_p()
+        # every step that can fail locally (IPC export / mapping) is followed by a collective vote, so
+        # that all ranks raise together and the caller can fall back to `HaloExchange` without a hang
         rc = self.lib.eqlb_halo_create(nn, counts, idxp, int(nrhs_max), C.byref(self.h), handle, send_off)
-        if rc != 0:
-            raise RuntimeError(self.lib.eqlb_last_error().decode())
-        mine = {"handle": bytes(handle), "neigh": [q for q, _ in self.neigh], "send_off": [int(v) for v in send_off[:nn]]}
+        err = self.lib.eqlb_last_error().decode() if rc != 0 else ""
+        mine = {"ok": rc == 0, "err": err, "handle": bytes(handle), "neigh": [q for q, _ in self.neigh],
+                "send_off": [int(v) for v in send_off[:nn]]}
         infos = [None] * world
         dist.all_gather_object(infos, mine, group=group)
+        if not all(i["ok"] for i in infos):
+            raise RuntimeError("P2PHaloExchange: " + "; ".join(i["err"] for i in infos if not i["ok"]))
+        ok, err = True, ""
         for n, (q, _) in enumerate(self.neigh):
             peer = infos[q]
             slot = peer["neigh"].index(rank)
             ph = (C.c_ubyte * 64).from_buffer_copy(peer["handle"])
-            rc = self.lib.eqlb_halo_connect(self.h, n, ph, peer["send_off"][slot], slot)
-            if rc != 0:
-                raise RuntimeError(self.lib.eqlb_last_error().decode())
+            if self.lib.eqlb_halo_connect(self.h, n, ph, peer["send_off"][slot], slot) != 0:
+                ok, err = False, self.lib.eqlb_last_error().decode()
+        votes = [None] * world
+        dist.all_gather_object(votes, (ok, err), group=group)
+        if not all(v[0] for v in votes):
+            raise RuntimeError("P2PHaloExchange: " + "; ".join(v[1] for v in votes if not v[0]))
         self.bytes_per_apply = sum(int(idx.size) * 8 for _, idx in self.neigh)
         dist.barrier(group=group)
 

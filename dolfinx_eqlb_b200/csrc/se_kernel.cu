@@ -389,20 +389,8 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
       }
       cf[a][0] += pm[a] * c_m;
       cf[a][k] += pp[a] * c_p;
-#ifdef EQLB_DEBUG
-      if (reversion)
-        printf("DBG2 node %d rhs %d a %d c_m %.8f c_p %.8f surf %.8f vol %.8f has_bc %d cf0 %.8f cfk %.8f\n", pv.node[ip], r, a, c_m,
-               c_p, surf, vol, (int)has_bc, cf[a][0], cf[a][k]);
-#endif
       c_prev = c_p;
     }
-#ifdef EQLB_DEBUG
-    if (reversion)
-    {
-      printf("DBG node %d rhs %d nc %d type %d ct1e0 %.10f pm0 %f pp0 %f pm1 %f pp1 %f mm0 %.6f mp0 %.6f mm1 %.6f mp1 %.6f cm0 %.6f cm1 %.6f\n",
-             pv.node[ip], r, nc, ptype, c_t1_e0, pm[0], pp[0], pm[1], pp[1], mm[0][0], mp[0][0], mm[1][0], mp[1][0], cm[0][0], cm[1][0]);
-    }
-#endif
     if (reversion)
     {
 #pragma unroll 1
@@ -655,10 +643,6 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
       }
     }
 
-#ifdef EQLB_DEBUG
-    if (reversion)
-      printf("DBG3 node %d rhs %d u0 %.8f A0 %.8f req_bc %d hz %d\n", pv.node[ip], r, L[0], A[0], (int)req_bc, hz);
-#endif
     // ---- map back to cell coefficients and accumulate ----
     double* __restrict__ sig = ptrs.S[r];
 #pragma unroll 1

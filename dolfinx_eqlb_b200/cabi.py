@@ -158,6 +158,10 @@ def load_library():
     lib.eqlb_get_ev_dofmaps.argtypes = [H, c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                         c_int32_p]
     lib.eqlb_get_ev_dofmaps.restype = C.c_int
+    lib.eqlb_pin_host.argtypes = [C.c_void_p, C.c_size_t]
+    lib.eqlb_pin_host.restype = C.c_int
+    lib.eqlb_unpin_host.argtypes = [C.c_void_p]
+    lib.eqlb_unpin_host.restype = C.c_int
     lib.eqlb_set_part.argtypes = [H, C.c_int]
     lib.eqlb_set_part.restype = C.c_int
     c_int64_p = C.POINTER(C.c_int64)

@@ -742,6 +742,41 @@ int eqlb_get_ev_dofmaps(eqlb_handle* h, int32_t* ncells, int32_t* cells, int32_t
       });
 }
 
+int eqlb_pin_host(void* ptr, size_t bytes)
+{
+  return guarded(
+      [&]
+      {
+        if (!ptr || bytes == 0)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_pin_host: null buffer");
+        require_device();
+        cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+        if (e == cudaErrorHostMemoryAlreadyRegistered)
+        {
+          cudaGetLastError();
+          return;
+        }
+        CUDA_CHECK(e);
+      });
+}
+
+int eqlb_unpin_host(void* ptr)
+{
+  return guarded(
+      [&]
+      {
+        if (!ptr)
+          return;
+        cudaError_t e = cudaHostUnregister(ptr);
+        if (e == cudaErrorHostMemoryNotRegistered)
+        {
+          cudaGetLastError();
+          return;
+        }
+        CUDA_CHECK(e);
+      });
+}
+
 int eqlb_set_part(eqlb_handle* h, int part)
 {
   return guarded(

@@ -265,6 +265,25 @@ class FluxEquilibrator:
         self.list_flux = []
         self.list_bfunctions = []
         self.boundary_data = None
+        self._pinned = []
+
+    def _pin(self, arrays, min_bytes=4 << 20):
+        """Page-lock large host vectors once (`eqlb_pin_host`) so that the host-pointer calls copy
+        at PCIe speed; small vectors are not worth the registration cost."""
+        lib = cabi.load_library()
+        for a in arrays:
+            if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.nbytes >= min_bytes:
+                if lib.eqlb_pin_host(a.ctypes.data, a.nbytes) == 0:
+                    self._pinned.append(a)
+
+    def __del__(self):
+        try:
+            lib = cabi.load_library()
+            for a in self._pinned:
+                lib.eqlb_unpin_host(a.ctypes.data)
+            self._pinned = []
+        except Exception:
+            pass
 
 
 class FluxEqlbSE(FluxEquilibrator):
@@ -285,6 +304,8 @@ class FluxEqlbSE(FluxEquilibrator):
                                 interface_first)
         self.list_flux = [np.zeros(msh.ncell * self.tables.nrt) for _ in range(self.n_fluxes)]
         self._fresh = True  # list_flux still holds the zeros it was created with
+        if host_pipeline:
+            self._pin(self.list_flux + list(list_rhs) + list(list_proj_flux))
 
     def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
@@ -323,6 +344,8 @@ class FluxEqlbEV(FluxEquilibrator):
         self.ndofs = msh.nfct * k + msh.ncell * (k * k - k)
         self.list_flux = [np.zeros(self.ndofs) for _ in range(self.n_fluxes)]
         self._fresh = True
+        if host_pipeline:
+            self._pin(self.list_flux + list(list_rhs) + list(list_proj_flux))
 
     def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):

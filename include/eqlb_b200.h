@@ -23,6 +23,7 @@
 #ifndef EQLB_B200_H
 #define EQLB_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -204,6 +205,12 @@ int eqlb_halo_connect(eqlb_halo* h, int n, const unsigned char* peer_ipc_handle,
                       int64_t peer_send_off, int peer_slot);
 int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream);
 void eqlb_halo_destroy(eqlb_halo* h);
+
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister): host-pointer calls on
+ * pageable memory are staged by the driver at a fraction of the PCIe rate.  Register the
+ * flux / RHS vectors once per function (e.g. the PETSc arrays), not per call. */
+int eqlb_pin_host(void* ptr, size_t bytes);
+int eqlb_unpin_host(void* ptr);
 
 /* number of kernel launches issued by this handle so far (bench "gpu_launches") */
 int64_t eqlb_launch_count(eqlb_handle* h);

@@ -158,6 +158,8 @@ def load_library():
     lib.eqlb_get_ev_dofmaps.argtypes = [H, c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                         c_int32_p]
     lib.eqlb_get_ev_dofmaps.restype = C.c_int
+    lib.eqlb_flux_l2norm.argtypes = [H, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int]
+    lib.eqlb_flux_l2norm.restype = C.c_int
     lib.eqlb_pin_host.argtypes = [C.c_void_p, C.c_size_t]
     lib.eqlb_pin_host.restype = C.c_int
     lib.eqlb_unpin_host.argtypes = [C.c_void_p]

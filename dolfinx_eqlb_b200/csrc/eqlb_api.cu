@@ -1002,6 +1002,48 @@ int eqlb_local_project(eqlb_handle* h, int nfun, const double* const* qvals, dou
       });
 }
 
+int eqlb_flux_l2norm(eqlb_handle* h, int nfun, const double* const* sigma, double* const* eta2, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !sigma || !eta2 || nfun < 1)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_flux_l2norm: bad argument");
+        if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_flux_l2norm: memspace must be EQLB_HOST or EQLB_DEVICE");
+        const size_t nin = (size_t)h->ncell * h->nrt, nout = (size_t)h->ncell;
+        std::vector<const double*> ds(nfun);
+        std::vector<double*> dout(nfun);
+        DevBuf<double> stage_in, stage_out;
+        if (memspace == EQLB_DEVICE)
+        {
+          for (int i = 0; i < nfun; ++i)
+          {
+            ds[i] = sigma[i];
+            dout[i] = eta2[i];
+          }
+        }
+        else
+        {
+          stage_in.alloc(nin * nfun);
+          stage_out.alloc(nout * nfun);
+          for (int i = 0; i < nfun; ++i)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(stage_in.p + i * nin, sigma[i], nin * 8, cudaMemcpyHostToDevice, h->stream));
+            ds[i] = stage_in.p + i * nin;
+            dout[i] = stage_out.p + i * nout;
+          }
+        }
+        launch_flux_norm(h, nfun, ds.data(), dout.data());
+        if (memspace != EQLB_DEVICE)
+        {
+          for (int i = 0; i < nfun; ++i)
+            CUDA_CHECK(cudaMemcpyAsync(eta2[i], dout[i], nout * 8, cudaMemcpyDeviceToHost, h->stream));
+          CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+      });
+}
+
 int64_t eqlb_launch_count(eqlb_handle* h) { return h ? h->launches : 0; }
 
 } // extern "C"

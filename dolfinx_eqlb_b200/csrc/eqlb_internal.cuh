@@ -244,6 +244,7 @@ void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF,
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma);
 void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* const* dout);
 void launch_korn(eqlb_handle* h, double* dKorn);
+void launch_flux_norm(eqlb_handle* h, int nfun, const double* const* dsig, double* const* dout);
 void build_k1_tables(eqlb_handle* h, const eqlb_tables* t);
 void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff);
 void build_k2_tables(eqlb_handle* h, const eqlb_tables* t);

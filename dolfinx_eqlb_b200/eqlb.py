@@ -321,6 +321,14 @@ class FluxEqlbSE(FluxEquilibrator):
         if self.estimate_korn_constant:
             self.korn_constants[:] = np.sqrt(self.korn_constants)
 
+    def flux_l2norm(self):
+        """Cell-wise ||sigma_i||^2_{L2(T)} of the equilibrated (DRT) fluxes: the flux part of the error
+        indicators of `demo_error_estimation.py:96-101`, evaluated on the GPU (`eqlb_flux_l2norm`)."""
+        out = [np.zeros(self.mesh.ncell) for _ in range(self.n_fluxes)]
+        _check(self.problem.lib, self.problem.lib.eqlb_flux_l2norm(self.problem.h, self.n_fluxes, cabi.ptr_array(self.list_flux),
+                                                                   cabi.ptr_array(out), 0))
+        return out
+
     def get_korn_constants(self):
         if self.estimate_korn_constant:
             return self.korn_constants

@@ -206,6 +206,13 @@ int eqlb_halo_connect(eqlb_halo* h, int n, const unsigned char* peer_ipc_handle,
 int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream);
 void eqlb_halo_destroy(eqlb_halo* h);
 
+/* Cell-wise squared L2 norm of DRT_k flux functions, eta2[i][cell] = ||sigma_i||^2_{L2(cell)}:
+ * the flux part `dot(err_sig, err_sig) * v * dx` of the reference's error indicators for the
+ * semi-explicit (discontinuous) flux (`python/demo/poisson/demo_error_estimation.py:96-101`),
+ * i.e. the consumer right after `equilibrate_fluxes`; with EQLB_DEVICE the flux never has to
+ * leave the GPU.  sigma[i] [ncell*nrt], eta2[i] [ncell] (assigned); EQLB_HOST or EQLB_DEVICE. */
+int eqlb_flux_l2norm(eqlb_handle* h, int nfun, const double* const* sigma, double* const* eta2, int memspace);
+
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister): host-pointer calls on
  * pageable memory are staged by the driver at a fraction of the PCIe rate.  Register the
  * flux / RHS vectors once per function (e.g. the PETSc arrays), not per call. */

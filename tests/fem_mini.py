@@ -326,3 +326,15 @@ def check_weak_symmetry(mesh, T, sig0, sig1):
     np.add.at(tot, mesh.cell_node.ravel(), loc.ravel())
     scale = np.einsum("q,c,cq->c", T.qwts, np.abs(det), np.abs(s0[..., 1]) + np.abs(s1[..., 0])).max()
     return np.abs(tot).max() / max(scale, 1e-300)
+
+
+def cell_l2norm_sq(mesh, T, sigma):
+    """Cell-wise ||sigma||^2_{L2(T)} of a DRT_k function by quadrature of the Piola-mapped basis
+    (J phi_hat / detJ): the UFL form `dot(sigma, sigma) * v * dx` with v in DG0."""
+    J, K, det = jacobians(mesh)
+    qp, qw = tb.cell_quadrature(2 * T.k)
+    phi, _ = tabulate_rt(T, qp)  # [q][nrt][2] reference values
+    c = sigma.reshape(mesh.ncell, T.nrt)
+    ref = np.einsum("ci,qid->cqd", c, phi)  # reference-cell combination
+    phys = np.einsum("cde,cqe->cqd", J, ref) / det[:, None, None]
+    return np.einsum("q,cqd,cqd->c", qw, phys, phys) * np.abs(det)

@@ -35,3 +35,22 @@ def test_projection_reproduces_polynomials():
     prob = eqlb._Problem(m, T, 1)
     got = eqlb.local_projection(prob, [qv])[0]
     assert np.abs(got - coef.ravel()).max() < 1e-12
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_flux_l2norm(k):
+    """Cell-wise ||sigma||^2 of the equilibrated DRT flux (error indicator of
+    demo_error_estimation.py:96-101) against quadrature of the mapped basis."""
+    import fem_mini as fm
+    from common import PoissonCase
+
+    m = make_mesh("crossed", 6, 3, perturb=0.3)
+    case = PoissonCase(m, k, [[1, 4], []], seed=2, galerkin=False)
+    eq = eqlb.FluxEqlbSE(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    eq.equilibrate_fluxes()
+    got = eq.flux_l2norm()
+    for r in range(case.nrhs):
+        ref = fm.cell_l2norm_sq(m, case.T, eq.list_flux[r])
+        assert np.abs(got[r] - ref).max() < 1e-12 * ref.max()
+        assert (got[r] >= 0.0).all()

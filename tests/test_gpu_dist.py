@@ -82,16 +82,18 @@ def _worker(rank, world, port, path, k, out, split=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("path,k,split", [("se", 2, False), ("ev", 2, False), ("se", 3, False), ("ev", 2, True), ("se", 1, True)])
-def test_two_gpu_halo_sum(path, k, split):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world,path,k,split", [(2, "se", 2, False), (2, "ev", 2, False), (2, "se", 3, False), (2, "ev", 2, True),
+                                                 (2, "se", 1, True), (4, "ev", 2, False), (4, "se", 2, True)])
+def test_multi_gpu_halo_sum(world, path, k, split):
+    """world = 4: the middle strips have two neighbours (flag slots, per-neighbour barriers)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(2, port, path, k, out, split), nprocs=2, join=True)
+        mp.spawn(_worker, args=(world, port, path, k, out, split), nprocs=world, join=True)
         res = dict(out)
-    assert len(res) == 2
+    assert len(res) == world
     for e in res.values():
         assert e < 1e-12
 

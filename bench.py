@@ -84,6 +84,7 @@ class ClockSampler(threading.Thread):
 # executed FP64 flop per patch (2*dfma + dmul + dadd, predicated-on thread instructions)
 NCU = {
     ("ev", 2, 1, False): {"traffic": 795.7e6, "flop_per_patch": 2897.0, "capture": "profiles/r1c_ev_k2w_ncu_full_summary.txt"},
+    ("se", 2, 1, False): {"traffic": 1013.7e6, "flop_per_patch": 2656.0, "capture": "profiles/r1c_se_k2w_ncu_full_summary.txt"},
 }
 FP64_PEAK_TFLOPS = 36.4  # measured FMA peak of this pool's B200 (profiles/peaks.cu, profiles/peaks_b200.txt)
 

@@ -425,7 +425,7 @@ def main():
                         "flop_per_patch": ncu["flop_per_patch"], "source": ncu["capture"],
                         "note": "executed FP64 flop (ncu) / step time; the kernel is FP64/issue bound, see DESIGN.md section 4"}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the CPU baseline is timed at N = 1 only
         v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress)
         cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": "port",
                "sample": f"{procs} processes x crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches each) of the same workload, mean of 3 steps"}

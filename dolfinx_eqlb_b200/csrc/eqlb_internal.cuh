@@ -13,6 +13,23 @@
 #define EQLB_NCMAX 16  // hard upper bound of cells per patch supported by the kernels
 #define EQLB_MAXRHS 8  // max number of simultaneously equilibrated fluxes
 
+// Reciprocal for the pivots / determinants of the patch kernels: hardware approximation
+// (MUFU.RCP64H, relative error 2^-23) + two Newton steps = full double precision for normal,
+// finite arguments in 5 instructions instead of the ~13 of the IEEE division sequence (no
+// denormal / infinity handling: pivots of SPD patch systems and cell determinants are neither).
+#ifdef __CUDACC__
+__device__ __forceinline__ double eqlb_rcp(double a)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+#endif
+
 // device pointers of the per-RHS vectors, passed by value as kernel parameter
 struct RhsPtrs
 {

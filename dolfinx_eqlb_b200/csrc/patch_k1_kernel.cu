@@ -74,7 +74,7 @@ patch_k1w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       const double2 j0 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c];
       const double2 j1 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c + 1];
       det = j0.x * j1.y - j0.y * j1.x;
-      const double iad = 1.0 / fabs(det);
+      const double iad = eqlb_rcp(fabs(det));
       adj[0] = j1.y;
       adj[1] = -j0.y;
       adj[2] = -j1.x;
@@ -164,7 +164,7 @@ patch_k1w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
           tot -= (first_c ? pm : pp) * bv0;
         tot = k1_seg_sum<S>(tot);
         if (valid && (internal || ptype == EQLB_PATCH_ESSNT_DUAL))
-          cm0 -= tot / (0.5 * area2) * det * s_mono;
+          cm0 -= tot * eqlb_rcp(0.5 * area2) * det * s_mono;
       }
 
       // ---- step 1 as a segmented scan ----
@@ -204,7 +204,7 @@ patch_k1w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       }
       const double a_zz = k1_seg_sum<S>(active ? M00 + M11 + 2.0 * p_em * p_ea * M01 : 0.0);
       const double l_z = k1_seg_sum<S>(active ? -(p_em * y0 + p_ea * y1) : 0.0);
-      const double u_z = (valid && !mark_z) ? l_z / a_zz : 0.0;
+      const double u_z = (valid && !mark_z) ? l_z * eqlb_rcp(a_zz) : 0.0;
 
       // ---- accumulate ----
       if (active)

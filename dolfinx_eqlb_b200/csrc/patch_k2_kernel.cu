@@ -63,7 +63,7 @@ __device__ __forceinline__ void load_cell(K2Cell& C, int32_t c, int info, const 
   const double f0 = Fv[3 * (size_t)c], f1 = Fv[3 * (size_t)c + 1], f2 = Fv[3 * (size_t)c + 2];
   const double J00 = j0.x, J01 = j0.y, J10 = j1.x, J11 = j1.y;
   const double det = J00 * J11 - J01 * J10;
-  const double iad = 1.0 / fabs(det);
+  const double iad = eqlb_rcp(fabs(det));
   C.det = det;
   C.adj[0] = J11;
   C.adj[1] = -J01;
@@ -704,7 +704,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       const double area2 = seg_sum<S>(active ? fabs(cur.det) : 0.0);
       if (valid && (internal || ptype == EQLB_PATCH_ESSNT_DUAL))
       {
-        const double lam = tot / (0.5 * area2);
+        const double lam = tot * eqlb_rcp(0.5 * area2);
 #pragma unroll
         for (int t = 0; t < K2_NT; ++t)
           cur.cm[t] -= lam * cur.det * s_mono[t];
@@ -896,7 +896,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
         g -= rG;
         w -= rW;
         l -= rL;
-        ipv = 1.0 / D;
+        ipv = eqlb_rcp(D);
         const double ei = e * ipv, gi = g * ipv, wi = w * ipv;
         oD = ei * e;
         oG = ei * g;
@@ -918,7 +918,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
     double u_F = 0.0, u_Z = 0.0, idet = 0.0;
     if (valid)
     {
-      idet = 1.0 / (S_FF * S_ZZ - S_FZ * S_FZ);
+      idet = eqlb_rcp(S_FF * S_ZZ - S_FZ * S_FZ);
       u_F = (l_F * S_ZZ - S_FZ * l_Z) * idet;
       u_Z = (S_FF * l_Z - S_FZ * l_F) * idet;
     }
@@ -1117,7 +1117,7 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
         for (int pv_ = 0; pv_ < S; ++pv_)
         {
           const double piv = __shfl_sync(FULL, Kr[pv_], pv_, S);
-          const double ip = 1.0 / piv;
+          const double ip = eqlb_rcp(piv);
           if (j == pv_)
             myip = ip;
           if (pv_ < S - 1)

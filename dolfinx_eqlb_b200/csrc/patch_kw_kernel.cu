@@ -72,7 +72,7 @@ __device__ __forceinline__ void inv_spd(const double (&A)[N][N], double (&Ai)[N]
 #pragma unroll
   for (int c = 0; c < N; ++c)
   {
-    const double ip = 1.0 / M[c][c];
+    const double ip = eqlb_rcp(M[c][c]);
 #pragma unroll
     for (int j = 0; j < N; ++j)
     {
@@ -145,7 +145,7 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
     const double2 j0 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c];
     const double2 j1 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)c + 1];
     det = j0.x * j1.y - j0.y * j1.x;
-    const double iad = 1.0 / fabs(det);
+    const double iad = eqlb_rcp(fabs(det));
     adj[0] = j1.y;
     adj[1] = -j0.y;
     adj[2] = -j1.x;
@@ -277,7 +277,7 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
       const double area2 = kw_seg_sum<S>(active ? fabs(det) : 0.0);
       if (valid && (internal || ptype == EQLB_PATCH_ESSNT_DUAL))
       {
-        const double lam = tot / (0.5 * area2);
+        const double lam = tot * eqlb_rcp(0.5 * area2);
 #pragma unroll
         for (int t = 0; t < NT; ++t)
           cm[t] -= lam * det * s_mono[t];

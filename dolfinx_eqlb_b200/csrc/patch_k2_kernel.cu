@@ -1,24 +1,19 @@
-// Streaming patch kernel for flux degree 2 with DG_1 data (the configuration of
+// Lane-per-cell patch kernel for flux degree 2 with DG_1 data (the configuration of
 // BASELINE.json configs 2, 4, 5).  Same mathematics as `patch_kernel` (se_kernel.cu:
 // reference se/solve_patch_semiexplt.hpp:212-1163 for SE, the null-space form of
-// ev/solve_patch.hpp:58-239 for EV) but organised around what the ncu capture of round 1
-// showed (profiles/README.md): the generic kernel keeps the dense patch system, all cell
-// geometry and all step-1 coefficients in a 2 KB per-thread stack frame that spills to
-// HBM (8.5 GB traffic per step against 0.67 GB algorithmic).  Here
-//   * cells are processed one at a time; nothing about a cell is kept except three
-//     doubles (zero-order coefficients on its two patch facets, higher-order one on E_a);
+// ev/solve_patch.hpp:58-239 for EV), organised around what the ncu captures of round 1
+// showed (profiles/README.md):
 //   * for k = 2 the patch system is "arrow + (cyclic) tridiagonal": one circulation dof
 //     d0 coupled to everything, one dof per patch facet coupled to its two neighbours.
 //     With facet E_0 (=: F) and d0 (=: Z) as a 2x2 border the remaining chain E_1..E_n is
-//     eliminated on the fly - facet E_a is complete as soon as cell T_a has been
-//     processed - so only five doubles per facet are kept for the back substitution;
-//   * this per-thread state (8 doubles per patch cell) lives in shared memory in
-//     [slot][thread] layout (bank-conflict free); the reference tables are pre-gathered
-//     per local facet pair (fm, fp) so that their reads are contiguous and warp-uniform
-//     on structured meshes;
-//   * SE needs the facet moments of the next cell (jump across E_a): one-cell lookahead.
+//     eliminated along the lanes;
+//   * the reference tables are pre-gathered per local facet pair (fm, fp) so that their
+//     reads are contiguous and warp-uniform on structured meshes.
 // Patches whose RHS may need the `reversion_required` correction (boundary patches of
-// multi-RHS problems) and stress equilibration stay on the generic kernel.
+// multi-RHS problems), the weak-symmetry stage of boundary patches and patches with more
+// than 16 facets stay on the generic kernel.
+// (An earlier per-thread streaming variant - one thread per patch, chain state in shared
+// memory, 1.9 ms/step - was superseded by the lane-per-cell kernel and removed.)
 #include "eqlb_internal.cuh"
 
 namespace
@@ -35,7 +30,6 @@ constexpr int K2_TAB = 6 * K2_BLOCK + 12;  // + dg_mono [3][3] + mono_int [3]
 // [q: lo0 lo1 hi0 hi1 div0 div1][d][j: patch node, outer node of E_a, outer node of E_{a-1}]
 constexpr int K2P_BLOCK = 50;  // 36 used; stride = 2 mod 16 doubles (bank-conflict free across combos)
 constexpr int K2_TAB_STRESS = K2_TAB + 6 * K2P_BLOCK;
-constexpr int K2_SLOTS = 8;                // per patch cell: ip,e,g,w,l of chain facet a+1 ; cz_m, cz_p, ch of cell a
 
 struct K2Cell
 {
@@ -142,433 +136,6 @@ __device__ __forceinline__ void patch_bc(const double* __restrict__ bsrc, const 
     bv1 = bc[2] * b0 + bc[3] * b1;
   }
 }
-
-template <bool EV>
-__global__ void __launch_bounds__(128)
-patch_k2_kernel(PatchView pv, int first, int count, const double* __restrict__ k2tab, const double* __restrict__ cellJ,
-                int nrhs, RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
-                const int32_t* __restrict__ cell_fct, int nfct)
-{
-  extern __shared__ double s_mem[];
-  double* s_blk = s_mem;                 // 6 combos x K2_BLOCK
-  double* s_dgm = s_mem + 6 * K2_BLOCK;  // [3][3]
-  double* s_mono = s_dgm + 9;            // [3]
-  double* s_state = s_mem + K2_TAB;      // [slot][thread]
-  for (int i = threadIdx.x; i < K2_TAB; i += blockDim.x)
-    s_mem[i] = k2tab[i];
-  __syncthreads();
-
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= count)
-    return;
-  const size_t ip = (size_t)first + tid;
-  const int nc = pv.ncells[ip];
-  const int nthr = blockDim.x;
-  double* st = s_state + threadIdx.x;
-#define ST(a, s) st[((a) * K2_SLOTS + (s)) * nthr]
-  constexpr int k = 2, nrt = 8;
-
-  for (int r = 0; r < nrhs; ++r)
-  {
-    const double* __restrict__ G = ptrs.G[r];
-    const double* __restrict__ Fv = ptrs.F[r];
-    double* __restrict__ sig = ptrs.S[r];
-    const uint8_t ri = pv.rhsinfo[(size_t)r * pv.stride + ip];
-    const int ptype = ri & 3;
-    const bool bc_e0 = (ri & 8) != 0, bc_en = (ri & 16) != 0;
-    const bool internal = (ptype == EQLB_PATCH_INTERNAL);
-    const bool req_bc = (ptype == EQLB_PATCH_ESSNT_DUAL || ptype == EQLB_PATCH_MIXED);
-    // constrained dofs (se/assembly.hpp:46-98); `reversion` never occurs on this kernel
-    const bool mark_z = req_bc, mark_f0 = req_bc, mark_fn = (ptype == EQLB_PATCH_ESSNT_DUAL);
-
-    // ---- EV: mean-value shift of the divergence data (ev/assembly.hpp:283-298) ----
-    double lam = 0.0;
-    if (EV && (internal || ptype == EQLB_PATCH_ESSNT_DUAL))
-    {
-      double tot = 0.0, area2 = 0.0;
-#pragma unroll 1
-      for (int a = 0; a < nc; ++a)
-      {
-        K2Cell T;
-        load_cell<EV>(T, pv.cell[(size_t)a * pv.stride + ip], pv.info[(size_t)a * pv.stride + ip], cellJ, G, Fv, s_blk, s_dgm);
-        tot += (T.det > 0.0 ? T.cm[0] : -T.cm[0]);
-        area2 += fabs(T.det);
-        if (!internal && (a == 0 || a == nc - 1))
-        {
-          const bool lastc = (a == nc - 1);
-          const int fm = (T.info >> 2) & 3, fp = (T.info >> 4) & 3;
-          double bv0, bv1;
-          patch_bc(bflux + (size_t)r * bflux_stride + (size_t)T.c * nrt + (lastc ? fp : fm) * k,
-                   s_blk + combo_of(fm, fp) * K2_BLOCK + K2_O_BC + (lastc ? 4 : 0), bv0, bv1);
-          tot -= (lastc ? T.pp : T.pm) * bv0;
-        }
-      }
-      lam = tot / (0.5 * area2);
-    }
-
-    // ---- streaming sweep: step 1, cell tensors, on-the-fly elimination ----
-    K2Cell cur, nxt;
-    load_cell<EV>(cur, pv.cell[ip], pv.info[ip], cellJ, G, Fv, s_blk, s_dgm);
-    const double first_mm0 = cur.mm[0], first_mm1 = cur.mm[1], first_pm = cur.pm;
-    double pp_prev = 0.0, mp0_prev = 0.0;
-    if (internal)
-    {
-      // outward sign of E_n = E_0 seen from the last cell (needed if E_0 is reversed)
-      const int32_t cl = pv.cell[(size_t)(nc - 1) * pv.stride + ip];
-      const int il = pv.info[(size_t)(nc - 1) * pv.stride + ip];
-      const double2 j0 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)cl];
-      const double2 j1 = reinterpret_cast<const double2*>(cellJ)[2 * (size_t)cl + 1];
-      const double sg = (j0.x * j1.y - j0.y * j1.x) > 0.0 ? 1.0 : -1.0;
-      pp_prev = (((il >> 4) & 3) == 1) ? sg : -sg;
-    }
-    double c_prev = 0.0;
-    double S_FF = 0.0, S_FZ = 0.0, S_ZZ = 0.0, l_F = 0.0, l_Z = 0.0;  // border: E_0 (F), d0 (Z)
-    double D_cur = 0.0, g_cur = 0.0, w_cur = 0.0, l_cur = 0.0;        // open chain facet
-    double ch0 = 0.0;                                                  // higher-order coefficient on E_0 (boundary)
-    uint32_t negdet = 0;
-
-#pragma unroll 1
-    for (int a = 0; a < nc; ++a)
-    {
-      const bool first_c = (a == 0), last_c = (a == nc - 1);
-      if (!last_c)
-        load_cell<EV>(nxt, pv.cell[(size_t)(a + 1) * pv.stride + ip], pv.info[(size_t)(a + 1) * pv.stride + ip], cellJ, G, Fv,
-                      s_blk, s_dgm);
-      const int fm = (cur.info >> 2) & 3, fp = (cur.info >> 4) & 3;
-      const bool rev0 = (cur.info & 64) != 0, rev1 = (cur.info & 128) != 0;
-      const double sgn = cur.det > 0.0 ? 1.0 : -1.0;
-      if (cur.det < 0.0)
-        negdet |= (1u << a);
-      const double* blk = s_blk + combo_of(fm, fp) * K2_BLOCK;
-      if (EV)
-      {
-#pragma unroll
-        for (int t = 0; t < K2_NT; ++t)
-          cur.cm[t] -= lam * cur.det * s_mono[t];
-      }
-      const bool on_bnd = !internal && (first_c || last_c);
-      bool has_bc = false;
-      if (on_bnd)
-      {
-        if (ptype == EQLB_PATCH_ESSNT_DUAL)
-          has_bc = true;
-        else if (ptype == EQLB_PATCH_MIXED)
-          has_bc = first_c ? bc_e0 : bc_en;
-      }
-      // sigma-tilde coefficients in the order [E_{a-1}: 0,1][E_a: 0,1][div: 0,1]
-      double cfv[6] = {0.0, 0.0, 0.0, 0.0, cur.cm[1], cur.cm[2]};
-      double c_m = -c_prev, surf = 0.0;
-      if (has_bc)
-      {
-        double bv0, bv1;
-        patch_bc(bflux + (size_t)r * bflux_stride + (size_t)cur.c * nrt + (first_c ? fm : fp) * k,
-                 blk + K2_O_BC + (first_c ? 0 : 4), bv0, bv1);
-        if (first_c)
-        {
-          c_m += cur.pm * bv0;
-          cfv[1] += bv1;
-        }
-        else
-          cfv[3] += bv1;
-      }
-      if (!EV)
-      {
-        if (!first_c)
-          surf = -cur.mm[0] - pp_prev * cur.pm * mp0_prev;
-        else if (!internal && (has_bc || ptype == EQLB_PATCH_MIXED))
-        {
-          cfv[1] += ((ptype == EQLB_PATCH_MIXED && !has_bc) ? 1.0 : -1.0) * cur.mm[1];
-          if (has_bc)
-            surf = -cur.mm[0];
-        }
-      }
-      c_m += cur.pm * surf;
-      const double c_p = -c_m + sgn * cur.cm[0];
-      if (!EV)
-      {
-        if (on_bnd && last_c)
-          cfv[3] += (has_bc ? -1.0 : 1.0) * cur.mp[1];
-        else
-        {
-          const double n_pm = last_c ? first_pm : nxt.pm;
-          const double n_m0 = last_c ? first_mm0 : nxt.mm[0], n_m1 = last_c ? first_mm1 : nxt.mm[1];
-          const double tau = -cur.pp * n_pm;
-          const double mt1 = rev1 ? (n_m0 - n_m1) : n_m1;  // binomial transform: s' = 1 - s
-          double h = tau * mt1 - cur.mp[1];
-          if (rev1 && !last_c)
-            h += -(tau * n_m0 - cur.mp[0]) + n_pm * c_p;
-          cfv[3] += h;
-        }
-      }
-      else if (rev1 && !last_c)
-        cfv[3] += nxt.pm * c_p;  // conformity of the particular solution across a reversed facet
-      cfv[0] += cur.pm * c_m;
-      cfv[2] += cur.pp * c_p;
-      c_prev = c_p;
-
-      // ---- cell block of the RT mass matrix (rows: E_{a-1} 0/1, E_a 0/1) and load ----
-      double MB[4][6];
-      {
-        const double* tm = blk + K2_O_MASS;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int s = 0; s < 6; ++s)
-            MB[q][s] = cur.g[0] * tm[q * 6 + s] + cur.g[1] * tm[24 + q * 6 + s] + cur.g[2] * tm[48 + q * 6 + s];
-      }
-      double y[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-      {
-        double s = 0.0;
-#pragma unroll
-        for (int c2 = 0; c2 < 6; ++c2)
-          s += MB[q][c2] * cfv[c2];
-        y[q] = s;
-      }
-      if (EV)
-      {
-        const double* hh = blk + K2_O_H;  // [m][q][2]
-#pragma unroll
-        for (int mI = 0; mI < 3; ++mI)
-        {
-          const double gx = cur.G[2 * mI], gy = cur.G[2 * mI + 1];
-          const double jg0 = sgn * (cur.adj[3] * gx - cur.adj[2] * gy);
-          const double jg1 = sgn * (-cur.adj[1] * gx + cur.adj[0] * gy);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            y[q] -= jg0 * hh[(mI * 4 + q) * 2] + jg1 * hh[(mI * 4 + q) * 2 + 1];
-        }
-      }
-      if (rev0)
-      {
-        // reversed E_{a-1}: R = [[-1,-1],[0,1]] on its two functions (rows/cols 0,1)
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          MB[0][s] = -MB[0][s] - MB[1][s];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          MB[q][0] = -MB[q][0] - MB[q][1];
-        y[0] = -y[0] - y[1];
-      }
-      const double p_ea = -cur.pp;
-      const double p_em = rev0 ? -pp_prev : cur.pm;
-      const double pe = p_em * p_ea;
-      // H(div=0) functions of the cell: 0: E_{a-1} higher, 1: d0, 2: E_a higher
-      const bool hi_is_F = internal && last_c;
-      const bool m_lo = first_c ? mark_f0 : false;
-      const bool m_hi = (!internal && last_c) ? mark_fn : false;
-      double T00 = MB[1][1], T22 = MB[3][3], T02 = pe * MB[1][3];
-      double T11 = MB[0][0] + MB[2][2] + 2.0 * pe * MB[0][2];
-      double T01 = MB[1][0] + pe * MB[1][2], T12 = pe * MB[3][0] + MB[3][2];
-      double l0 = -p_em * y[1], l1 = -(p_em * y[0] + p_ea * y[2]), l2 = -p_ea * y[3];
-      if (m_lo)
-        T00 = T01 = T02 = l0 = 0.0;
-      if (m_hi)
-        T22 = T12 = T02 = l2 = 0.0;
-      if (mark_z)
-        T11 = T01 = T12 = l1 = 0.0;
-      S_ZZ += T11;
-      l_Z += l1;
-      double D_new = 0.0, g_new = 0.0, w_new = 0.0, l_new = 0.0, e = 0.0;
-      if (first_c)
-      {
-        S_FF += T00;
-        S_FZ += T01;
-        l_F += l0;
-        g_new = T02;
-      }
-      else
-      {
-        D_cur += T00;
-        w_cur += T01;
-        l_cur += l0;
-        if (hi_is_F)
-          g_cur += T02;
-        else
-          e = T02;
-      }
-      if (hi_is_F)
-      {
-        S_FF += T22;
-        S_FZ += T12;
-        l_F += l2;
-      }
-      else
-      {
-        D_new = T22;
-        w_new = T12;
-        l_new = l2;
-      }
-      if (!first_c)
-      {
-        // chain facet E_a (lo side of this cell) is complete: eliminate it
-        const double ipv = 1.0 / D_cur;
-        ST(a - 1, 0) = ipv;
-        ST(a - 1, 1) = e;
-        ST(a - 1, 2) = g_cur;
-        ST(a - 1, 3) = w_cur;
-        ST(a - 1, 4) = l_cur;
-        const double ei = e * ipv, gi = g_cur * ipv, wi = w_cur * ipv;
-        D_new -= ei * e;
-        g_new -= ei * g_cur;
-        w_new -= ei * w_cur;
-        l_new -= ei * l_cur;
-        S_FF -= gi * g_cur;
-        S_FZ -= gi * w_cur;
-        S_ZZ -= wi * w_cur;
-        l_F -= gi * l_cur;
-        l_Z -= wi * l_cur;
-      }
-      D_cur = D_new;
-      g_cur = g_new;
-      w_cur = w_new;
-      l_cur = l_new;
-      // what pass 2 needs from step 1
-      ST(a, 5) = cfv[0];
-      ST(a, 6) = cfv[2];
-      ST(a, 7) = cfv[3];
-      if (first_c)
-        ch0 = cfv[1];
-      // divergence moments are final: accumulate right away
-      {
-        double* dstc = EV ? (sig + (size_t)nfct * k + (size_t)cur.c * 2) : (sig + (size_t)cur.c * nrt + 6);
-        if (use_atomics)
-        {
-          atomicAdd(dstc, cfv[4]);
-          atomicAdd(dstc + 1, cfv[5]);
-        }
-        else
-        {
-          dstc[0] += cfv[4];
-          dstc[1] += cfv[5];
-        }
-      }
-      pp_prev = cur.pp;
-      mp0_prev = cur.mp[0];
-      cur = nxt;
-    }
-    const int nch = internal ? nc - 1 : nc;  // chain facets E_1 .. E_nch
-    if (!internal)
-    {
-      // last boundary facet E_n (only cell T_n contributes)
-      if (mark_fn)
-      {
-        D_cur = 1.0;
-        g_cur = w_cur = l_cur = 0.0;
-      }
-      const double ipv = 1.0 / D_cur;
-      ST(nc - 1, 0) = ipv;
-      ST(nc - 1, 1) = 0.0;
-      ST(nc - 1, 2) = g_cur;
-      ST(nc - 1, 3) = w_cur;
-      ST(nc - 1, 4) = l_cur;
-      const double gi = g_cur * ipv, wi = w_cur * ipv;
-      S_FF -= gi * g_cur;
-      S_FZ -= gi * w_cur;
-      S_ZZ -= wi * w_cur;
-      l_F -= gi * l_cur;
-      l_Z -= wi * l_cur;
-    }
-    if (mark_z)
-      S_ZZ = 1.0;
-    if (mark_f0)
-      S_FF = 1.0;
-    const double idet = 1.0 / (S_FF * S_ZZ - S_FZ * S_FZ);
-    const double u_F = (l_F * S_ZZ - S_FZ * l_Z) * idet;
-    const double u_Z = (S_FF * l_Z - S_FZ * l_F) * idet;
-    {
-      double u_next = 0.0;
-      for (int b = nch; b >= 1; --b)
-      {
-        const double ub = (ST(b - 1, 4) - ST(b - 1, 1) * u_next - ST(b - 1, 2) * u_F - ST(b - 1, 3) * u_Z) * ST(b - 1, 0);
-        ST(b - 1, 0) = ub;
-        u_next = ub;
-      }
-    }
-
-    // ---- pass 2: map back to cell coefficients and accumulate ----
-    double pp_before = 0.0;
-    if (internal)
-    {
-      const int il = pv.info[(size_t)(nc - 1) * pv.stride + ip];
-      const double sg = (negdet >> (nc - 1)) & 1u ? -1.0 : 1.0;
-      pp_before = (((il >> 4) & 3) == 1) ? sg : -sg;
-    }
-#pragma unroll 1
-    for (int a = 0; a < nc; ++a)
-    {
-      const int32_t c = pv.cell[(size_t)a * pv.stride + ip];
-      const int inf = pv.info[(size_t)a * pv.stride + ip];
-      const int fm = (inf >> 2) & 3, fp = (inf >> 4) & 3;
-      const bool rev0 = (inf & 64) != 0;
-      const double sgn = (negdet >> a) & 1u ? -1.0 : 1.0;
-      const double pm = (fm == 1) ? sgn : -sgn, pp = (fp == 1) ? sgn : -sgn;
-      const double p_ea = -pp;
-      const double p_em = rev0 ? -pp_before : pm;
-      pp_before = pp;
-      const double u_lo = (a == 0) ? u_F : ST(a - 1, 0);
-      const double u_hi = (internal && a == nc - 1) ? u_F : ST(a, 0);
-      double um0 = p_em * u_Z, um1 = p_em * u_lo;
-      if (rev0)
-      {
-        const double t0 = -um0, t1 = -um0 + um1;  // R^T
-        um0 = t0;
-        um1 = t1;
-      }
-      const double up0 = p_ea * u_Z, up1 = p_ea * u_hi;
-      const double clo0 = ST(a, 5) + um0, clo1 = (a == 0 ? ch0 : 0.0) + um1;
-      const double chi0 = ST(a, 6) + up0, chi1 = ST(a, 7) + up1;
-      if (EV)
-      {
-        // conforming vector: T_a owns facet E_a (hi side), T_1 of a boundary patch also E_0
-        for (int side = (a == 0 && !internal) ? 0 : 1; side < 2; ++side)
-        {
-          const int fl = side ? fp : fm;
-          const bool refl = (inf & (side ? 512 : 256)) != 0;
-          const double cl0 = side ? chi0 : clo0, cl1 = side ? chi1 : clo1;
-          const double cg0 = refl ? -cl0 : cl0;         // c_g = R^T c_loc
-          const double cg1 = refl ? (-cl0 + cl1) : cl1;
-          double* d = sig + (size_t)cell_fct[3 * (size_t)c + fl] * k;
-          if (use_atomics)
-          {
-            atomicAdd(d, cg0);
-            atomicAdd(d + 1, cg1);
-          }
-          else
-          {
-            d[0] += cg0;
-            d[1] += cg1;
-          }
-        }
-      }
-      else
-      {
-        double* d = sig + (size_t)c * nrt;
-        if (use_atomics)
-        {
-          atomicAdd(d + fm * 2, clo0);
-          atomicAdd(d + fm * 2 + 1, clo1);
-          atomicAdd(d + fp * 2, chi0);
-          atomicAdd(d + fp * 2 + 1, chi1);
-        }
-        else
-        {
-          double2* d2 = reinterpret_cast<double2*>(d);
-          double2 vlo = d2[fm], vhi = d2[fp];
-          vlo.x += clo0;
-          vlo.y += clo1;
-          vhi.x += chi0;
-          vhi.y += chi1;
-          d2[fm] = vlo;
-          d2[fp] = vhi;
-        }
-      }
-    }
-  }
-#undef ST
-}
-
 
 // ---------------------------------------------------------------------------
 // Warp-cooperative variant: S lanes per patch, ONE LANE PER PATCH CELL.
@@ -1326,7 +893,7 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
   const int bs = 128;
   const PatchView pv = h->patch_view();
   const size_t bstride = (size_t)h->ncell * h->nrt;
-  if (lanes > 0 && recoff >= 0 && !(h->flags & EQLB_FLAG_K2_THREAD))
+  if (lanes > 0 && recoff >= 0)
   {
     // warp-cooperative kernel: S lanes per patch
     const size_t smem = (size_t)K2_TAB * sizeof(double);
@@ -1363,13 +930,7 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
                                         use_atomics, h->d_prec.p + recoff, h->nfct, nwt);
   }
   else
-  {
-    const size_t smem = ((size_t)K2_TAB + (size_t)K2_SLOTS * h->ncmax * bs) * sizeof(double);
-    auto kern = patch_k2_kernel<EV>;
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(count + bs - 1) / bs, bs, smem, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs,
-                                                        h->d_bflux.p, bstride, use_atomics, h->d_cell_fct.p, h->nfct);
-  }
+    throw EqlbError(EQLB_ERR_STATE, "degree-2 kernel: segment without lane records");
   CUDA_CHECK(cudaGetLastError());
   h->launches++;
 }

@@ -29,7 +29,6 @@ __device__ __constant__ double c_nref[3][2] = {{-1.0, -1.0}, {-1.0, 0.0}, {0.0, 
 template <int K>
 struct SeDims
 {
-  static constexpr int k = K;
   static constexpr int ndiv = K * (K + 1) / 2 - 1;
   static constexpr int nadd = (K - 1) * (K - 2) / 2;
   static constexpr int nrt = K * (K + 2);

@@ -50,7 +50,7 @@ extern "C" {
 #define EQLB_FLAG_STRESS 1u   /* first gdim fluxes are rows of a stress tensor (weak symmetry) */
 #define EQLB_FLAG_ATOMIC 2u   /* accumulate with fp64 atomics instead of colour-ordered launches */
 #define EQLB_FLAG_GENERIC 4u  /* always use the generic patch kernel (no degree-2 streaming kernel) */
-#define EQLB_FLAG_K2_THREAD 8u /* degree 2: thread-per-patch streaming kernel instead of lane-per-cell */
+#define EQLB_FLAG_K2_THREAD 8u /* reserved (former per-thread degree-2 kernel, removed); ignored */
 /* host-pointer calls stream the mesh through the GPU in spatial stages: host->device copy of
  * stage s+1, patch kernels of stage s and device->host copy of finished DOF ranges overlap on
  * three streams (PCIe both directions busy); costs a few extra launches on device-pointer calls */

@@ -118,3 +118,42 @@ def test_errors_like_reference():
     m = ms.build_topology(x, np.array([[0, 1, 3], [0, 2, 3]]))
     with pytest.raises(RuntimeError, match="has only 1 cells"):
         eqlb.FluxEqlbSE(1, m, [np.zeros(2)], [np.zeros(4)])
+
+
+@pytest.mark.parametrize("env", [{"EQLB_KW": "1"}, {"EQLB_RED": "0"}, {"EQLB_STRESS_GENERIC": "1"}])
+def test_alternate_kernel_switches(env):
+    """The environment switches are read once per process, so the alternate paths run in a
+    child process: degree 2 on the general-degree kernel, load-add-store accumulation,
+    generic weak-symmetry stage - all against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, 'tests')
+from common import PoissonCase, make_mesh
+from test_gpu_stress import elasticity_case
+from dolfinx_eqlb_b200 import eqlb
+from oracle import pyoracle as po
+m = make_mesh('crossed', 6, 3, perturb=0.2)
+case = PoissonCase(m, 2, [[1, 4]], seed=7)
+for cls, ref in ((eqlb.FluxEqlbSE, po.se_run), (eqlb.FluxEqlbEV, po.ev_run)):
+    eq = cls(2, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    eq.equilibrate_fluxes()
+    r = ref(m, case.T, case.oracle_bc(), case.G, case.F)[0]
+    assert np.abs(eq.list_flux[0] - r).max() < 1e-10 * np.abs(r).max()
+T, G, f, bfp, bcs, neu = elasticity_case(m, 2, [], seed=3)
+eq = eqlb.FluxEqlbSE(2, m, f, G, equilibrate_stress=True)
+eq.set_boundary_conditions(bfp, bcs)
+bd = eq.boundary_data
+r = po.se_run(m, T, po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd), G, f, stress=True)
+eq.equilibrate_fluxes()
+for i in range(2):
+    assert np.abs(eq.list_flux[i] - r[i]).max() < 1e-10 * np.abs(r[i]).max()
+print('ok')
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

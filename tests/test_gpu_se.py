@@ -157,3 +157,68 @@ print('ok')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def fan_mesh(nfan, seed=0):
+    """Disc triangulated as two rings: a central vertex of valence `nfan` (one interior patch
+    with nfan cells -> the 16-lane variants of the lane-per-cell kernels for nfan > 8)."""
+    from dolfinx_eqlb_b200 import mesh as ms
+
+    rng = np.random.default_rng(seed)
+    ang = 2 * np.pi * (np.arange(nfan) + 0.15 * rng.random(nfan)) / nfan
+    inner = 0.5 * np.stack([np.cos(ang), np.sin(ang)], 1)
+    outer = 1.0 * np.stack([np.cos(ang + np.pi / nfan), np.sin(ang + np.pi / nfan)], 1)
+    x = np.concatenate([[[0.0, 0.0]], inner, outer])
+    tris = []
+    for i in range(nfan):
+        a, b = 1 + i, 1 + (i + 1) % nfan
+        o = 1 + nfan + i
+        tris += [[0, a, b], [a, o, b], [b, o, 1 + nfan + (i + 1) % nfan]]
+    perm = rng.permutation(x.shape[0])  # scrambled vertex numbering: reversed facets, negative Jacobians
+    inv = np.argsort(perm)
+    return ms.build_topology(x[perm], inv[np.array(tris)].astype(np.int32))
+
+
+@pytest.mark.parametrize("nfan", [9, 13, 16])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_high_valence_patches(nfan, k):
+    """Patches with 9..16 cells take the S = 16 lane variants; parity against the oracle for SE, EV
+    and (k = 2) the fused weak-symmetry stage."""
+    from oracle import pyoracle as po
+    from dolfinx_eqlb_b200 import tables as tb
+
+    m = fan_mesh(nfan, seed=nfan)
+    T = tb.make_tables(k)
+    rng = np.random.default_rng(k)
+    nrhs = 2
+    G = [rng.standard_normal(m.ncell * T.ndg * 2) for _ in range(nrhs)]
+    F = [rng.standard_normal(m.ncell * T.ndg) for _ in range(nrhs)]
+    bf = [m.bfct.astype(np.int32)] * nrhs
+    ft = np.zeros((nrhs, m.nfct), np.int8)
+    ft[:, m.bfct] = 1
+    bc = po.BCData(ft)
+    for cls, ref in ((eqlb.FluxEqlbSE, po.se_run), (eqlb.FluxEqlbEV, po.ev_run)):
+        eq = cls(k, m, F, G)
+        eq.set_boundary_conditions(bf, [[], []])
+        eq.equilibrate_fluxes()
+        r = ref(m, T, bc, G, F)
+        for i in range(nrhs):
+            assert np.abs(eq.list_flux[i] - r[i]).max() < 1e-10 * np.abs(r[i]).max()
+    if k == 2:
+        eq = eqlb.FluxEqlbSE(k, m, F, G, equilibrate_stress=True)
+        eq.set_boundary_conditions(bf, [[], []])
+        eq.equilibrate_fluxes()
+        r = po.se_run(m, T, po.BCData(ft, None, None, np.zeros(m.nnode, np.int8)), G, F, stress=True)
+        for i in range(nrhs):
+            assert np.abs(eq.list_flux[i] - r[i]).max() < 1e-10 * np.abs(r[i]).max()
+
+
+def test_too_many_cells_is_an_error():
+    """More than 16 cells around a vertex: rejected loudly by eqlb_create (no silent fallback)."""
+    from dolfinx_eqlb_b200 import tables as tb
+
+    m = fan_mesh(17, seed=1)
+    T = tb.make_tables(2)
+    z = [np.zeros(m.ncell * T.ndg)]
+    with pytest.raises(RuntimeError, match="more than 16 cells"):
+        eqlb.FluxEqlbSE(2, m, z, [np.zeros(m.ncell * T.ndg * 2)])

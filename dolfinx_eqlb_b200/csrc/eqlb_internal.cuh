@@ -269,4 +269,4 @@ bool kw_supported(int k, int ndg);
 void build_kw_tables(eqlb_handle* h, const eqlb_tables* t);
 void launch_kw(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff);
 void launch_k2(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int maxnf, int lanes,
-               int64_t recoff, bool stress);
+               int64_t recoff, bool stress, bool pdl);

@@ -1302,6 +1302,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   }
   else
   {
+    bool launched_before = false;  // a kernel of this call precedes the next launch in the stream
     for (int c = std::max(0, h->win_lo); c < std::min(h->nseg, h->win_hi); ++c)
     {
       int first = h->h_colour_off[c];
@@ -1322,9 +1323,16 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
         if (K == 1)
           launch_k1(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);
         else if (K == 2 && (!force_kw || stress))
-          launch_k2(h, EV, ptrs, first, nfast, use_red, h->h_colour_maxnf[c], h->h_seg_lanes[c], h->h_seg_recoff[c], stress);
+        {
+          // programmatic dependent launch behind a kernel of this very call (never behind foreign work
+          // that may still be producing G or f)
+          static const bool pdl_on = getenv("EQLB_PDL") ? atoi(getenv("EQLB_PDL")) != 0 : true;
+          launch_k2(h, EV, ptrs, first, nfast, use_red, h->h_colour_maxnf[c], h->h_seg_lanes[c], h->h_seg_recoff[c], stress,
+                    pdl_on && launched_before && use_red);
+        }
         else
           launch_kw(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);
+        launched_before = launched_before || nfast > 0;
         first += nfast;
         count -= nfast;
       }
@@ -1334,6 +1342,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
                                                           h->d_bflux.p, bstride, 0, h->d_cell_fct.p, h->nfct, 0);
       CUDA_CHECK(cudaGetLastError());
       h->launches++;
+      launched_before = true;
     }
   }
 }

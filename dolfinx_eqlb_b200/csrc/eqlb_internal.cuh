@@ -263,7 +263,8 @@ void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* c
 void launch_korn(eqlb_handle* h, double* dKorn);
 void launch_flux_norm(eqlb_handle* h, int nfun, const double* const* dsig, double* const* dout);
 void build_k1_tables(eqlb_handle* h, const eqlb_tables* t);
-void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff);
+void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff,
+               bool pdl);
 void build_k2_tables(eqlb_handle* h, const eqlb_tables* t);
 bool kw_supported(int k, int ndg);
 void build_kw_tables(eqlb_handle* h, const eqlb_tables* t);

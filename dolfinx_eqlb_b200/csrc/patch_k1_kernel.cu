@@ -41,6 +41,10 @@ patch_k1w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
     s_tab[i] = tab[i];
   __syncthreads();
   const double s_dgm = s_tab[6 * K1_BLOCK], s_mono = s_tab[6 * K1_BLOCK + 1];
+  // programmatic dependent launch (see patch_k2_kernel.cu): the next colour starts while this one
+  // drains and waits right before its first update of sigma
+  asm volatile("griddepcontrol.launch_dependents;");
+  bool dep_pending = true;
 
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int PPW = 32 / S;
@@ -207,6 +211,11 @@ patch_k1w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
       const double u_z = (valid && !mark_z) ? l_z * eqlb_rcp(a_zz) : 0.0;
 
       // ---- accumulate ----
+      if (dep_pending)
+      {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        dep_pending = false;
+      }
       if (active)
       {
         const double olo = c_lo + p_em * u_z, ohi = c_hi + p_ea * u_z;
@@ -248,7 +257,7 @@ patch_k1w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
 }
 
 template <bool EV>
-void launch_k1_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int S, int64_t recoff)
+void launch_k1_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int S, int64_t recoff, bool pdl)
 {
   if ((S != 4 && S != 8 && S != 16) || recoff < 0)
     throw EqlbError(EQLB_ERR_STATE, "degree-1 kernel: segment without lane records");
@@ -258,8 +267,20 @@ void launch_k1_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int 
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
   const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * 6));
   auto kern = (S == 4) ? patch_k1w_kernel<EV, 4> : (S == 8 ? patch_k1w_kernel<EV, 8> : patch_k1w_kernel<EV, 16>);
-  kern<<<grid, bs, 0, h->stream>>>(h->patch_view(), first, count, h->d_k1tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p,
-                                   (size_t)h->ncell * h->nrt, use_atomics, h->d_prec.p + recoff, nwt);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(bs);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;  // only behind one of our own launches of the same call (launch_patch_t)
+  const PatchView pv = h->patch_view();
+  const double *tabp = h->d_k1tab.p, *cj = h->d_cellJ.p, *bfl = h->d_bflux.p;
+  const int4* recp = h->d_prec.p + recoff;
+  const size_t bstride = (size_t)h->ncell * h->nrt;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, pv, first, count, tabp, cj, h->nrhs, ptrs, bfl, bstride, use_atomics, recp, nwt));
   CUDA_CHECK(cudaGetLastError());
   h->launches++;
 }
@@ -301,12 +322,13 @@ void build_k1_tables(eqlb_handle* h, const eqlb_tables* t)
   h->d_k1tab.upload(tab.data(), tab.size());
 }
 
-void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff)
+void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff,
+               bool pdl)
 {
   if (count <= 0)
     return;
   if (ev)
-    launch_k1_t<true>(h, ptrs, first, count, use_atomics, lanes, recoff);
+    launch_k1_t<true>(h, ptrs, first, count, use_atomics, lanes, recoff, pdl);
   else
-    launch_k1_t<false>(h, ptrs, first, count, use_atomics, lanes, recoff);
+    launch_k1_t<false>(h, ptrs, first, count, use_atomics, lanes, recoff, pdl);
 }

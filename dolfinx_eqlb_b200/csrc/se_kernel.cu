@@ -1320,13 +1320,13 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
         // serialised on the stream); measured 14-25 % faster than load-add-store.
         static const int use_red = getenv("EQLB_RED") ? atoi(getenv("EQLB_RED")) : 1;
         const int nfast = h->h_colour_fast[c];
+        // programmatic dependent launch behind a kernel of this very call (never behind foreign work
+        // that may still be producing G or f)
+        static const bool pdl_on = getenv("EQLB_PDL") ? atoi(getenv("EQLB_PDL")) != 0 : true;
         if (K == 1)
-          launch_k1(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);
+          launch_k1(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c], pdl_on && launched_before && use_red);
         else if (K == 2 && (!force_kw || stress))
         {
-          // programmatic dependent launch behind a kernel of this very call (never behind foreign work
-          // that may still be producing G or f)
-          static const bool pdl_on = getenv("EQLB_PDL") ? atoi(getenv("EQLB_PDL")) != 0 : true;
           launch_k2(h, EV, ptrs, first, nfast, use_red, h->h_colour_maxnf[c], h->h_seg_lanes[c], h->h_seg_recoff[c], stress,
                     pdl_on && launched_before && use_red);
         }

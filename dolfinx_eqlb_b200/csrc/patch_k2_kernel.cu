@@ -187,11 +187,12 @@ patch_k2w_kernel(PatchView pv, int first, int count, const double* __restrict__ 
   [[maybe_unused]] double cf0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // stress row 0, kept until row 1 is done
   // EV: programmatic dependent launch - the next colour may start (tables, records, cell data, the
   // arithmetic of its first tile) while this one drains; it waits right before its first update of
-  // sigma.  Measured 0.740 -> 0.722 ms/step; for the SE instantiation the same branch costs more
-  // than it gains (0.763 -> 0.806 ms), so it is compiled for EV only.
+  // sigma.  Measured 0.740 -> 0.722 ms/step; for the SE instantiation the same in-loop branch costs
+  // more than it gains (0.763 -> 0.806 ms), so SE waits right here after the prologue instead.
   [[maybe_unused]] bool dep_pending = true;
-  if constexpr (EV)
-    asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.launch_dependents;");
+  if constexpr (!EV)
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // SE: only launch latency and the table staging overlap
 
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int PPW = 32 / S;
@@ -950,7 +951,7 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
-    cfg.numAttrs = (EV && pdl) ? 1 : 0;  // only behind one of our own launches of the same call (launch_patch_t)
+    cfg.numAttrs = pdl ? 1 : 0;  // only behind one of our own launches of the same call (launch_patch_t)
     const double* bfl = h->d_bflux.p;
     const int4* recp = h->d_prec.p + recoff;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, pv, first, count, (const double*)h->d_k2tab.p, (const double*)h->d_cellJ.p, h->nrhs,

@@ -52,7 +52,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.stamps, self.reasons, self.max_mhz = [], [], set(), None
         self._halt = threading.Event()
 
     def run(self):
@@ -64,19 +64,24 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0]))
+                self.stamps.append(time.time())
                 self.max_mhz = float(out[1])
                 for nm, v in zip(names, out[2:]):
                     if "Active" in v and "Not" not in v:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.02)
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock of the samples taken inside the timed region [t0, t1] (all samples if none fell inside)."""
         self._halt.set()
         self.join(timeout=5)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        inside = [v for v, t in zip(self.samples, self.stamps) if t0 is not None and t0 <= t <= t1]
+        use = inside or self.samples
+        med = float(np.median(use)) if use else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples_in_timed_region": len(inside), "samples": len(self.samples)}
 
 
 # ncu evidence of the dominant kernel (profiles/README.md), keyed by (path, k, nrhs, stress) at n = 1024:
@@ -197,14 +202,15 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default=os.environ.get("EQLB_BENCH_PATH", "ev"), choices=["se", "ev"])
     ap.add_argument("--k", type=int, default=2)
     ap.add_argument("--nrhs", type=int, default=1)
     ap.add_argument("--n", type=int, default=1024)
-    ap.add_argument("--cpu-n", type=int, default=256, dest="cpu_n")
+    ap.add_argument("--cpu-n", type=int, default=None, dest="cpu_n",
+                    help="edge length of the CPU sample mesh per process (default: 256, shrunk so that the reference arm's steps+warmup fit ~90 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stress", action="store_true", help="SE with weak symmetry: nrhs >= 2 rows of a stress tensor")
     args = ap.parse_args()
@@ -212,6 +218,14 @@ def main():
     if args.stress:
         args.path, args.nrhs = "se", max(args.nrhs, 2)
 
+    if args.cpu_n is None:
+        args.cpu_n = 256
+        if args.impl == "reference" and int(os.environ.get("RANK", "0")) == 0:
+            # calibrate on a 64 x 64 block (all processes busy), then size the sample so that the whole
+            # run (steps + warm-up) takes about 90 s; the cost per step grows like n^2
+            _, _, sec64, _ = time_oracle(args.path, 64, args.k, max(args.nrhs, 2) if args.stress else args.nrhs, 1, 0, stress=args.stress)
+            budget = 90.0 / max(args.steps + args.warmup, 1)
+            args.cpu_n = int(max(32, min(256, 64 * (budget / sec64) ** 0.5)) // 8 * 8)
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -328,11 +342,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_wall0 = time.time()
     l0 = prob.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -342,7 +357,7 @@ def main():
     barrier()
     launches = prob.launch_count() - l0
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, time.time())
     if dist is not None:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

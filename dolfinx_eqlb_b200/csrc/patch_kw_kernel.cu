@@ -395,7 +395,10 @@ patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ t
 #pragma unroll
         for (int s2 = 0; s2 < ncol; ++s2)
         {
-          const double mv = gmm[0] * tm[q * ncol + s2] + gmm[1] * tm[(nact + q) * ncol + s2] + gmm[2] * tm[(2 * nact + q) * ncol + s2];
+          // the square block is symmetric (the three reference matrices are): reuse the transposed entry
+          const double mv = (s2 < q && s2 < nact) ? MQ[s2][q]
+                                                  : gmm[0] * tm[q * ncol + s2] + gmm[1] * tm[(nact + q) * ncol + s2]
+                                                        + gmm[2] * tm[(2 * nact + q) * ncol + s2];
           acc += mv * cfv[s2];
           if (s2 < nact)
             MQ[q][s2] = mv;

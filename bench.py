@@ -86,7 +86,8 @@ class ClockSampler(threading.Thread):
 
 # ncu evidence of the dominant kernel (profiles/README.md), keyed by (path, k, nrhs, stress) at n = 1024:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the colour launches of one step) and
-# executed FP64 flop per patch (2*dfma + dmul + dadd, predicated-on thread instructions)
+# executed FP64 flop per patch (2*dfma + dmul + dadd, predicated-on thread instructions).  The captures predate
+# the last two kernel steps (reciprocal sequence, symmetric mass block), which removed about 2 % of these flops.
 NCU = {
     ("ev", 2, 1, False): {"traffic": 795.7e6, "flop_per_patch": 2897.0, "capture": "profiles/r1c_ev_k2w_ncu_full_summary.txt"},
     ("se", 2, 1, False): {"traffic": 1013.7e6, "flop_per_patch": 2656.0, "capture": "profiles/r1c_se_k2w_ncu_full_summary.txt"},

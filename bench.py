@@ -56,6 +56,40 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
+    def _run_nvml(self):
+        """NVML polling (about 1 ms per sample): enough samples even for a few-millisecond timed region."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {
+                "hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap,
+            }
+            while not self._halt.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.stamps.append(time.time())
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for nm, b in bits.items():
+                        if r & b:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                self._halt.wait(0.002)
+        finally:
+            nv.nvmlShutdown()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]

@@ -1,8 +1,14 @@
-"""Generates tests/golden/*.npz.  The reference ships no golden vectors and
-cannot be imported here, so the vectors are produced by the oracle from seeded inputs
-on the reference's own fixture sizes (2x2 / 5x5 crossed unit squares,
-test_fluxeqlb_conditions.py:47-49) and accepted only if the reference's acceptance
-invariants hold.  Run from the repo root:  python tests/golden/make_golden.py"""
+"""Generates tests/golden/*.npz.  The reference ships no golden vectors.
+
+SE and stress fixtures (`se_*`, `stress_*`) are OUTPUTS OF THE REFERENCE ITSELF: its own C++
+sources compiled unchanged against stand-in headers (`oracle/_ref/libeqlb_ref.so`, recipe
+`make -C oracle ref`, needs /root/reference) run on seeded inputs on the reference's own
+fixture sizes (2x2 / 5x5 crossed unit squares, test_fluxeqlb_conditions.py:47-49); the
+files carry `source = "reference"`.  EV fixtures (`ev_*`) come from the oracle (the EV
+numerics need FFCx-generated kernels, which cannot be produced offline; the EV integer
+maps are pinned against the reference's ev::Patch in tests/test_ref_pinning.py).  Every
+vector is accepted only if the reference's acceptance invariants hold.
+Run from the repo root (build container):  python tests/golden/make_golden.py"""
 
 import os
 import sys
@@ -16,6 +22,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fem_mini as fm  # noqa: E402
 from common import PoissonCase, make_mesh  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
+from oracle import pyref as pr  # noqa: E402
 
 CASES = [
     # name, path, kind, n, scramble, perturb, k, neumann sets, seed
@@ -58,7 +65,7 @@ def main():
         name, path = spec[0], spec[1]
         m, case = build(*spec)
         if path == "se":
-            sig = po.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+            sig = pr.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
             for r in range(case.nrhs):
                 assert fm.check_divergence(m, case.T, sig[r], case.G[r], case.F[r]) < 1e-12
                 assert fm.check_jump(m, case.T, sig[r], case.G[r]) < 1e-12
@@ -69,9 +76,10 @@ def main():
                 z = np.zeros_like(case.G[r])
                 assert fm.check_divergence(m, case.T, s, z, case.F[r]) < 1e-10
                 assert fm.check_jump(m, case.T, s, z) < 1e-12
-        maps = po.se_patch_maps(m, case.T, case.oracle_bc())
+        maps = (pr if path == "se" else po).se_patch_maps(m, case.T, case.oracle_bc())
         np.savez_compressed(
             os.path.join(out, name + ".npz"), G=np.array(case.G), F=np.array(case.F), sigma=np.array(sig),
+            source=np.array("reference" if path == "se" else "oracle"),
             cells=maps["cells"], fcts=maps["fcts"], type=maps["type"], fcts_local=maps["fcts_local"],
             reversed=maps["reversed"], cell_node=m.cell_node, x=m.x,
         )
@@ -79,14 +87,14 @@ def main():
     for spec in STRESS_CASES:
         m, T, G, f, bfp, bcs, bd = build_stress(*spec)
         bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
-        sig, korn = po.se_run(m, T, bc, G, f, stress=True, korn=True)
+        sig, korn = pr.se_run(m, T, bc, G, f, stress=True, korn=True)
         for r in range(2):
             assert fm.check_divergence(m, T, sig[r], G[r], f[r]) < 1e-12
             assert fm.check_jump(m, T, sig[r], G[r]) < 1e-10
         ws = fm.check_weak_symmetry(m, T, sig[0], sig[1])
         assert ws < 1e-10, (spec[0], ws)
         np.savez_compressed(os.path.join(out, spec[0] + ".npz"), G=np.array(G), F=np.array(f), sigma=np.array(sig), korn=korn,
-                            cell_node=m.cell_node, x=m.x)
+                            cell_node=m.cell_node, x=m.x, source=np.array("reference"))
         print("wrote", spec[0])
 
 

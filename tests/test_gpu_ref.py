@@ -1,0 +1,78 @@
+"""GPU parity against the reference's OWN code (`oracle/_ref/libeqlb_ref.so`: the reference
+sources compiled unchanged, see tests/test_ref_pinning.py): device patch maps / SE 4-plane
+DOF maps / EV sub-DOF maps bit-exact, SE and stress flux DOFs within 1e-10 relative
+(BASELINE.json north_star).  The library is built in the build container and travels with
+the snapshot; the tests skip if it is absent."""
+
+import numpy as np
+import pytest
+
+from common import PoissonCase, make_mesh
+from dolfinx_eqlb_b200 import eqlb
+from oracle import pyref as pr
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not pr.available(), reason="oracle/_ref not available")]
+RTOL = 1e-10
+MESHES = [("crossed", 4, None), ("crossed", 5, 3), ("randdiag", 6, 2)]
+INT_KEYS = ["ncells", "cells", "fcts", "inodes_local", "fcts_local", "type", "reversed", "reversion"]
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("kind,n,scramble", MESHES)
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_se_maps_and_flux_vs_reference(kind, n, scramble, k):
+    m = make_mesh(kind, n, scramble, perturb=0.2)
+    case = PoissonCase(m, k, [[1, 4], [1, 3], [2], [1, 3, 4]], seed=5)
+    bc = case.oracle_bc()
+    ref_maps = pr.se_patch_maps(m, case.T, bc)
+    ref = pr.se_run(m, case.T, bc, case.G, case.F)
+    eq = eqlb.FluxEqlbSE(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    got = eq.problem.patch_maps()
+    for key in INT_KEYS:
+        assert np.array_equal(got[key], ref_maps[key]), key
+    dm = eq.problem.se_dofmaps()
+    for key in ["dofmap", "projflux_fct", "bmarkers"]:
+        assert np.array_equal(dm[key], ref_maps[key]), key
+    eq.equilibrate_fluxes()
+    for r in range(case.nrhs):
+        assert rel_err(eq.list_flux[r], ref[r]) < RTOL
+
+
+@pytest.mark.parametrize("kind,n,scramble", MESHES)
+@pytest.mark.parametrize("k,nsides", [(2, []), (3, []), (2, [1]), (3, [1]), (3, [1, 2]), (3, [2, 3, 4]), (2, [1, 3]), (2, [1, 2]),
+                                      (2, [2, 3, 4]), (2, [3]), (2, [2, 4]), (3, [1, 2, 4]), (2, [1, 4]), (3, [3, 4])])
+def test_stress_vs_reference(kind, n, scramble, k, nsides):
+    from oracle import pyoracle as po
+    from test_gpu_stress import elasticity_case
+
+    m = make_mesh(kind, n, scramble, perturb=0.2)
+    T, G, f, bfp, bcs, neu = elasticity_case(m, k, nsides, seed=3, galerkin=False)
+    eq = eqlb.FluxEqlbSE(k, m, f, G, equilibrate_stress=True, estimate_korn_constant=True)
+    eq.set_boundary_conditions(bfp, bcs)
+    bd = eq.boundary_data
+    bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
+    ref, kref = pr.se_run(m, T, bc, G, f, stress=True, korn=True)
+    eq.equilibrate_fluxes()
+    for r in range(2):
+        assert rel_err(eq.list_flux[r], ref[r]) < RTOL
+    assert rel_err(eq.get_korn_constants(), np.sqrt(kref)) < 1e-12
+
+
+@pytest.mark.parametrize("kind,n,scramble", MESHES)
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_ev_dofmaps_vs_reference(kind, n, scramble, k):
+    m = make_mesh(kind, n, scramble, perturb=0.2)
+    case = PoissonCase(m, k, [[1, 4], [2]], seed=5, galerkin=False)
+    eq = eqlb.FluxEqlbEV(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    got = eq.problem.ev_dofmaps()
+    bc = case.oracle_bc()
+    for z in range(m.nnode):
+        ref = pr.ev_patch_maps(m, case.T, bc, z)
+        assert got["ncells"][z] == ref["ncells"]
+        for key in ("cells", "fcts", "inodes_local", "dofs_elmt", "dofs_patch", "dofs_global", "list_patch", "list_global"):
+            assert np.array_equal(got[key][z], ref[key]), (z, key)

@@ -1,12 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the equilibration hot path: equilibrated patches / second.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--path ev|se] [--n 1024]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 1|2|3|4] [--path ev|se] [--n 1024]
 
 One "step" = one equilibrate_fluxes()-equivalent call (all patches of the mesh,
-patch maps resident, inputs resident in HBM).  Workload at N=1: BASELINE.json
-configs[1] (Poisson, flux degree 2, 1024x1024 crossed unit square, pure
-Dirichlet, synthetic random coefficients).  Prints ONE JSON line on rank 0.
+patch maps resident, inputs resident in HBM).  Workload at N=1 (default, `--config 1`):
+BASELINE.json configs[1] (Poisson, FluxEqlbEV, flux degree 2, 1024x1024 crossed unit square,
+pure Dirichlet, synthetic random coefficients; N > 1: weak scaling, one such block per GPU).
+`--config 2..4` = BASELINE.json configs[2..4] at their stated sizes, STRONG-scaled over the
+N GPUs (the global mesh is fixed, cut into N strips of rows):
+  2  Poisson FluxEqlbSE, degree 3, 4096x4096, mixed flux BCs (sides 1,4 traction with random
+     DG_2 data, sides 2,3 Dirichlet: `python/test/unit/testcase_general.py:251-272`)
+  3  linear elasticity, 2 stress rows + weak symmetry, degree 2, 2048x2048, pure Dirichlet
+  4  Biot: 2 stress rows + Darcy flux (3 RHS), weak symmetry, degree 2, 4096x4096
+Prints ONE JSON line on rank 0.  At N > 1 the line carries `halo_check`: the halo-summed result
+of a small partitioned problem of the same kind against the single-GPU result (max relative
+error; the run fails above 1e-12).
 """
 
 from __future__ import annotations
@@ -118,15 +127,44 @@ class ClockSampler(threading.Thread):
                 "samples_in_timed_region": len(inside), "samples": len(self.samples)}
 
 
-# ncu evidence of the dominant kernel (profiles/README.md), keyed by (path, k, nrhs, stress) at n = 1024:
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (mean of the colour launches of one step) and
-# executed FP64 flop per patch (2*dfma + dmul + dadd, predicated-on thread instructions).  The captures predate
-# the last two kernel steps (reciprocal sequence, symmetric mass block), which removed about 2 % of these flops.
-NCU = {
-    ("ev", 2, 1, False): {"traffic": 795.7e6, "flop_per_patch": 2897.0, "capture": "profiles/r1c_ev_k2w_ncu_full_summary.txt"},
-    ("se", 2, 1, False): {"traffic": 1013.7e6, "flop_per_patch": 2656.0, "capture": "profiles/r1c_se_k2w_ncu_full_summary.txt"},
+CONFIGS = {
+    # BASELINE.json configs[i]: path, k, nrhs, n, stress, traction sides
+    1: dict(path="ev", k=2, nrhs=1, n=1024, stress=False, neumann=[]),
+    2: dict(path="se", k=3, nrhs=1, n=4096, stress=False, neumann=[1, 4]),
+    3: dict(path="se", k=2, nrhs=2, n=2048, stress=True, neumann=[]),
+    4: dict(path="se", k=2, nrhs=3, n=4096, stress=True, neumann=[]),
 }
-FP64_PEAK_TFLOPS = 36.4  # measured FMA peak of this pool's B200 (profiles/peaks.cu, profiles/peaks_b200.txt)
+
+KERNEL_SOURCES = ["patch_k2_kernel.cu", "patch_kw_kernel.cu", "patch_k1_kernel.cu", "se_kernel.cu", "eqlb_internal.cuh"]
+
+
+def kernel_source_hash():
+    """sha256 over the kernel sources: ncu numbers in profiles/ncu_kernels.json are only printed
+    for the sources they were captured from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "dolfinx_eqlb_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_record(key):
+    """ncu evidence of the dominant kernel of a workload (dram bytes per launch, executed FP64 flop per
+    patch) from profiles/ncu_kernels.json (written by tools/ncu_summary.py from a `ncu --set full`
+    capture of this very bench command); None if there is no capture or it is stale."""
+    p = os.path.join(ROOT, "profiles", "ncu_kernels.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as fh:
+        db = json.load(fh)
+    rec = db.get(key)
+    if rec is None:
+        return None
+    if rec.get("kernel_source_hash") != kernel_source_hash():
+        return {"stale": True, "capture": rec.get("capture"), "kernel_source_hash": rec.get("kernel_source_hash")}
+    return rec
 
 
 def peaks():
@@ -137,26 +175,43 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def build_case(n, k, nrhs):
-    from dolfinx_eqlb_b200 import eqlb, mesh as ms, tables as tb
+def boundary_conditions(m, T, nrhs, neumann, seed=SEED + 1):
+    """(list_bfct_prime, list_bcs): `neumann` sides carry a traction with random DG_{k-1} data
+    (`2 (U + 0.1)`, testcase_general.py:263-272), the other sides are Dirichlet sides of the primal problem."""
+    from dolfinx_eqlb_b200 import eqlb
+
+    dsides = [s for s in (1, 2, 3, 4) if s not in neumann]
+    bfct = [m.boundary_facets(dsides) for _ in range(nrhs)]
+    bcs = []
+    rng = np.random.default_rng(seed)
+    for _ in range(nrhs):
+        if neumann:
+            fcts = m.boundary_facets(neumann)
+            bcs.append([eqlb.fluxbc(fcts, 2.0 * (rng.random((fcts.shape[0], T.k)) + 0.1))] if fcts.size else [])
+        else:
+            bcs.append([])
+    return bfct, bcs
+
+
+def build_case(n, k, nrhs, neumann=(), fast=None):
+    from dolfinx_eqlb_b200 import mesh as ms, tables as tb
 
     T = tb.make_tables(k)
-    m = ms.crossed_unit_square(n)
+    m = ms.crossed_unit_square(n, fast=(n > 1024) if fast is None else fast)
     G, F = synthetic_inputs(m.ncell, T.ndg, nrhs)
-    bfct = [m.boundary_facets([1, 2, 3, 4]) for _ in range(nrhs)]
-    bcs = [[] for _ in range(nrhs)]
+    bfct, bcs = boundary_conditions(m, T, nrhs, list(neumann))
     return m, T, G, F, bfct, bcs
 
 
-def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue, stress=False):
+def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue, stress=False, neumann=()):
     """One host process = one rank of the reference's MPI-parallel CPU path: it equilibrates
     its own n x n block (no communication: an upper bound of the reference's scaling)."""
     from oracle import pyoracle as po
-    from dolfinx_eqlb_b200 import mesh as ms
+    from dolfinx_eqlb_b200 import eqlb
 
-    m, T, G, F, bfct, bcs = build_case(n, k, nrhs)
-    ft = np.stack([ms.facet_types(m, [1, 2, 3, 4], []) for _ in range(nrhs)])
-    bc = po.BCData(ft)
+    m, T, G, F, bfct, bcs = build_case(n, k, nrhs, neumann, fast=False)
+    bd = eqlb.boundarydata(bcs, m, T, bfct, stress)
+    bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
     run = (lambda: po.se_run(m, T, bc, G, F, stress=stress)) if path == "se" else (lambda: po.ev_run(m, T, bc, G, F))
     for _ in range(warmup):
         run()
@@ -176,7 +231,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None, stress=False):
+def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None, stress=False, neumann=()):
     """CPU baseline: the oracle restatement (reference loop structure) on a bounded sample
     of the same workload, one process per host core like the reference under mpirun.
     Returns (patches/s over all processes, patches per process, seconds per step, processes)."""
@@ -185,7 +240,7 @@ def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None, stress=False):
     procs = procs or min(host_cores(), 128)
     ctx = mp.get_context("spawn")
     barrier, queue = ctx.Barrier(procs), ctx.Queue()
-    ws = [ctx.Process(target=_oracle_worker, args=(path, n, k, nrhs, warmup, steps, barrier, queue, stress)) for _ in range(procs)]
+    ws = [ctx.Process(target=_oracle_worker, args=(path, n, k, nrhs, warmup, steps, barrier, queue, stress, tuple(neumann))) for _ in range(procs)]
     for w in ws:
         w.start()
     res = [queue.get() for _ in ws]
@@ -206,14 +261,15 @@ def reference_arm(args):
         return
     n_sample = args.cpu_n
     t0 = time.perf_counter()
-    value, npatch, sec, procs = time_oracle(args.path, n_sample, args.k, args.nrhs, args.steps, max(args.warmup, 0), stress=args.stress)
+    value, npatch, sec, procs = time_oracle(args.path, n_sample, args.k, args.nrhs, args.steps, max(args.warmup, 0), stress=args.stress,
+                                            neumann=args.neumann)
     total = time.perf_counter() - t0
     sample = (f"{procs} processes x crossed {n_sample}x{n_sample} ({npatch} patches each) of the {args.n}x{args.n} workload, "
               f"mean of {args.steps} steps, step = slowest process")
     line = {
         "impl": "reference", "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": scaling_mode(args), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,16 +278,107 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def scaling_mode(args):
+    """config 1: weak (one 1024^2 block per GPU); configs 2-4: strong (BASELINE sizes are global)."""
+    return "weak" if args.config == 1 else "strong"
+
+
 def workload_config(args):
-    name = {"ev": "Poisson FluxEqlbEV, P2 primal / RT2 flux", "se": "Poisson FluxEqlbSE"}[args.path]
+    """Identical for every N and for both arms (the driver compares `config` across runs)."""
+    name = {"ev": f"Poisson FluxEqlbEV, P{args.k} primal / RT{args.k} flux", "se": f"Poisson FluxEqlbSE, P{args.k} primal / RT{args.k} flux"}[args.path]
     if getattr(args, "stress", False):
-        name = "Linear elasticity stress equilibration with weak symmetry (FluxEqlbSE)"
+        name = ("Linear elasticity stress equilibration with weak symmetry (FluxEqlbSE)" if args.nrhs == 2
+                else "Poro-elasticity (Biot): stress rows + Darcy flux, weak symmetry (FluxEqlbSE)")
+    bcs = "pure Dirichlet" if not args.neumann else f"mixed fluxbc (sides {args.neumann} traction with random DG_{args.k - 1} data, other sides Dirichlet)"
+    size = f"{args.n}x{args.n} crossed unit square" + (" per GPU" if args.config == 1 else " (global)")
     return {
-        "workload": f"{name}, degree_flux={args.k}, {args.n}x{args.n} crossed unit square, pure Dirichlet, nrhs={args.nrhs}",
-        "path": args.path, "degree_flux": args.k, "n": args.n, "nrhs": args.nrhs,
+        "workload": f"BASELINE configs[{args.config}]: {name}, degree_flux={args.k}, {size}, {bcs}, nrhs={args.nrhs}",
+        "path": args.path, "degree_flux": args.k, "n": args.n, "nrhs": args.nrhs, "bcs": bcs,
         "l2": "inputs larger than L2 (no flush needed)", "accumulation": "colour-ordered (deterministic)",
-        "parallelism": "vertex strips, owner-computes patches, halo sum over NVLink peer memory" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "single GPU",
+        "parallelism": "single GPU at N=1; N>1: vertex strips, owner-computes patches, halo sum over NVLink peer memory",
     }
+
+
+def halo_check(args, rank, world, dist_mod):
+    """Driver-visible multi-GPU correctness: a small problem of the benchmarked kind (same path, degree, RHS
+    count, BC layout) is partitioned over the ranks, equilibrated, halo-summed - and compared with the
+    single-GPU result of the whole mesh computed redundantly on every rank.  Returns the max relative error
+    over all ranks and RHS."""
+    import torch
+
+    from dolfinx_eqlb_b200 import dist as dd, eqlb, mesh as ms, tables as tb
+
+    k, nrhs = args.k, args.nrhs
+    T = tb.make_tables(k)
+    n = 8 * world
+    gm = ms.crossed_unit_square(n)
+    G, F = synthetic_inputs(gm.ncell, T.ndg, nrhs, seed=SEED + 7)
+    gbf, gbc = boundary_conditions(gm, T, nrhs, args.neumann, seed=SEED + 9)
+    cls = eqlb.FluxEqlbSE if args.path == "se" else eqlb.FluxEqlbEV
+    kw = {"equilibrate_stress": True} if args.stress else {}
+    geq = cls(k, gm, F, G, **kw)
+    geq.set_boundary_conditions(gbf, gbc)
+    geq.equilibrate_fluxes()
+    part, _ = dd.crossed_rows(n, rank, world, fast=False)
+    lm = part.mesh
+    cg = part.cell_gid
+    lG = [g.reshape(gm.ncell, -1)[cg].ravel() for g in G]
+    lF = [f.reshape(gm.ncell, -1)[cg].ravel() for f in F]
+    # local BCs: the global boundary data restricted to the local facets (same traction coefficients)
+    gkey = gm.fct_node[:, 0].astype(np.int64) * gm.nnode + gm.fct_node[:, 1]
+    lkey = part.fct_gid(gm.nnode)
+    l2g_f = np.searchsorted(gkey, lkey)
+    lbf, lbc = [], []
+    for r in range(nrhs):
+        gset = np.zeros(gm.nfct, dtype=bool)
+        gset[gbf[r]] = True
+        lbf.append(np.nonzero(gset[l2g_f])[0].astype(np.int32))
+        bl = []
+        for bc in gbc[r]:
+            row = np.full(gm.nfct, -1, dtype=np.int64)
+            row[bc.facets] = np.arange(bc.facets.shape[0])
+            sel = np.nonzero(row[l2g_f] >= 0)[0].astype(np.int32)
+            if sel.size:
+                bl.append(eqlb.fluxbc(sel, bc.coeffs[row[l2g_f[sel]]]))
+        lbc.append(bl)
+    leq = cls(k, lm, lF, lG, node_owned=part.node_owned, **kw)
+    leq.set_boundary_conditions(lbf, lbc)
+    leq.equilibrate_fluxes()
+    if args.path == "se":
+        loc, gid = dd.se_dof_gids(part, T.nrt)
+    else:
+        loc, gid = dd.ev_dof_gids(part, k, gm.nnode)
+    xs = [torch.from_numpy(np.ascontiguousarray(s)).cuda() for s in leq.list_flux]
+    try:
+        hx = dd.P2PHaloExchange(loc, gid, nrhs_max=nrhs) if os.environ.get("EQLB_HALO", "p2p") != "nccl" else dd.HaloExchange(loc, gid, device="cuda")
+    except RuntimeError:
+        hx = dd.HaloExchange(loc, gid, device="cuda")
+    hx.apply(xs)
+    torch.cuda.synchronize()
+    # compared: the DOFs of all local cells with at least one owned vertex (a rank's copy of the other halo
+    # cells - e.g. the bottom triangles of the halo row - receives no contribution and is never read)
+    live_c = part.node_owned[lm.cell_node].any(axis=1)
+    live_f = np.zeros(lm.nfct, dtype=bool)
+    live_f[lm.cell_fct[live_c].ravel()] = True
+    err = 0.0
+    for r in range(nrhs):
+        got = xs[r].cpu().numpy()
+        ref = geq.list_flux[r]
+        if args.path == "se":
+            want = ref.reshape(gm.ncell, T.nrt)[cg]
+            d = np.abs(got.reshape(lm.ncell, T.nrt) - want)[live_c]
+        else:
+            ncd = k * k - k
+            wf = ref[: gm.nfct * k].reshape(gm.nfct, k)[l2g_f]
+            wc = ref[gm.nfct * k :].reshape(gm.ncell, ncd)[cg]
+            want = np.concatenate([wf.ravel(), wc.ravel()])
+            d = np.concatenate([np.abs(got[: lm.nfct * k].reshape(lm.nfct, k) - wf)[live_f].ravel(),
+                                np.abs(got[lm.nfct * k :].reshape(lm.ncell, ncd) - wc)[live_c].ravel()])
+        err = max(err, float(d.max() / max(np.abs(want).max(), 1e-300)))
+    t = torch.tensor([err], device="cuda", dtype=torch.float64)
+    dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    del hx
+    return float(t.item())
 
 
 def main():
@@ -240,16 +387,26 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--path", default=os.environ.get("EQLB_BENCH_PATH", "ev"), choices=["se", "ev"])
-    ap.add_argument("--k", type=int, default=2)
-    ap.add_argument("--nrhs", type=int, default=1)
-    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--config", type=int, default=int(os.environ.get("EQLB_BENCH_CONFIG", "1")), choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[i]; --path/--k/--nrhs/--n/--stress override single fields")
+    ap.add_argument("--path", default=None, choices=["se", "ev"])
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--nrhs", type=int, default=None)
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--neumann", type=str, default=None, help="comma separated traction sides, e.g. 1,4")
     ap.add_argument("--cpu-n", type=int, default=None, dest="cpu_n",
                     help="edge length of the CPU sample mesh per process (default: 256, shrunk so that the reference arm's steps+warmup fit ~90 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stress", action="store_true", help="SE with weak symmetry: nrhs >= 2 rows of a stress tensor")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg0 = CONFIGS[args.config]
+    args.path = args.path or os.environ.get("EQLB_BENCH_PATH") or cfg0["path"]
+    args.k = args.k or cfg0["k"]
+    args.nrhs = args.nrhs or cfg0["nrhs"]
+    args.n = args.n or cfg0["n"]
+    args.stress = args.stress or cfg0["stress"]
+    args.neumann = [int(s) for s in args.neumann.split(",") if s] if args.neumann is not None else list(cfg0["neumann"])
     if args.stress:
         args.path, args.nrhs = "se", max(args.nrhs, 2)
 
@@ -258,7 +415,7 @@ def main():
         if args.impl == "reference" and int(os.environ.get("RANK", "0")) == 0:
             # calibrate on a 64 x 64 block (all processes busy), then size the sample so that the whole
             # run (steps + warm-up) takes about 90 s; the cost per step grows like n^2
-            _, _, sec64, _ = time_oracle(args.path, 64, args.k, max(args.nrhs, 2) if args.stress else args.nrhs, 1, 0, stress=args.stress)
+            _, _, sec64, _ = time_oracle(args.path, 64, args.k, args.nrhs, 1, 0, stress=args.stress, neumann=args.neumann)
             budget = 90.0 / max(args.steps + args.warmup, 1)
             args.cpu_n = int(max(32, min(256, 64 * (budget / sec64) ** 0.5)) // 8 * 8)
     if args.impl == "reference":
@@ -283,18 +440,21 @@ def main():
     k, nrhs = args.k, args.nrhs
     node_owned, part, nnode_global = None, None, None
     if world == 1:
-        m, T, G, F, bfct, bcs = build_case(args.n, args.k, args.nrhs)
+        m, T, G, F, bfct, bcs = build_case(args.n, args.k, args.nrhs, args.neumann)
         npatch_total = m.nnode
     else:
-        # weak scaling: `world` stacked n x n blocks, strip-partitioned by vertex rows
         from dolfinx_eqlb_b200 import dist as dd, tables as tb
 
         T = tb.make_tables(k)
-        part, nnode_global = dd.crossed_strip(args.n, rank, world)
+        if args.config == 1:
+            # weak scaling: `world` stacked n x n blocks, strip-partitioned by vertex rows
+            part, nnode_global = dd.crossed_strip(args.n, rank, world)
+        else:
+            # strong scaling: the n x n mesh of the config cut into `world` strips of rows
+            part, nnode_global = dd.crossed_rows(args.n, rank, world)
         m, node_owned = part.mesh, part.node_owned
         G, F = synthetic_inputs(m.ncell, T.ndg, nrhs, seed=SEED + rank)
-        bfct = [m.bfct[m.bfct_side > 0].astype(np.int32) for _ in range(nrhs)]
-        bcs = [[] for _ in range(nrhs)]
+        bfct, bcs = boundary_conditions(m, T, nrhs, args.neumann, seed=SEED + 1 + rank)
         npatch_total = nnode_global
     if args.path == "se":
         eq = eqlb.FluxEqlbSE(k, m, F, G, node_owned=node_owned, host_pipeline=False, equilibrate_stress=args.stress,
@@ -321,7 +481,7 @@ def main():
 
     pG, pF, pS = dptrs(dG), dptrs(dF), dptrs(dS)
 
-    hx = None
+    hx, halo_name = None, None
     if world > 1:
         if args.path == "se":
             loc, gid = dd.se_dof_gids(part, T.nrt)
@@ -337,6 +497,8 @@ def main():
                 if rank == 0:
                     print(f"[bench] peer-memory halo unavailable ({e}); using NCCL send/recv", file=sys.stderr)
                 hx = dd.HaloExchange(loc, gid, device="cuda")
+
+    halo_name = type(hx).__name__ if hx is not None else None
 
     def run_device():
         if args.path == "se":
@@ -450,50 +612,73 @@ def main():
     h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF)
     d2h = sum(s.numel() * 8 for s in hS)
 
+    hcheck = None
     if dist is not None:
+        del hx
+        torch.cuda.synchronize()
+        dist.barrier()
+        hcheck = halo_check(args, rank, world, dist)
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
+        if hcheck is not None and not (hcheck <= 1e-12):
+            sys.exit(3)
         return
     # ---- roofline of the dominant kernel (the patch kernel is the whole step) ----
     peak, peak_src = peaks()
     bpc = alg_bytes_per_cell(k, T.ndg, T.nrt, nrhs, args.path)
     alg_bytes_step = bpc * m.ncell  # per rank
     achieved = alg_bytes_step / (ms_step * 1e-3) / 1e9
-    ncu = NCU.get((args.path, k, nrhs, bool(args.stress))) if (args.n == 1024 and world == 1) else None
+    ncu_key = f"config{args.config}" if (args.n == CONFIGS[args.config]["n"] and args.path == CONFIGS[args.config]["path"]
+                                         and k == CONFIGS[args.config]["k"]) else None
+    ncu = ncu_record(ncu_key) if (ncu_key and world == 1) else None
     lps = launches / args.steps
     roof = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu["traffic"] if ncu else None,
-        "kernel": "patch_k2w_kernel" if k == 2 else ("patch_kw_kernel" if k == 3 else "patch_kernel"),
+        "traffic": ncu["traffic"] if (ncu and not ncu.get("stale")) else None,
+        "kernel": (ncu or {}).get("kernel") or ("patch_k2w_kernel" if k == 2 else ("patch_kw_kernel" if k == 3 else "patch_kernel")),
         "alg_bytes_per_patch": bpc * m.ncell / m.nnode, "alg_bytes_per_launch": alg_bytes_step / lps,
         "avg_launch_ms": ms_step / lps, "peak_source": peak_src, "launches_per_step": lps,
+        "kernel_source_hash": kernel_source_hash(),
     }
-    if ncu:
+    if ncu and ncu.get("stale"):
+        roof["ncu"] = "stale capture (kernel sources changed since profiles/ncu_kernels.json was written): traffic/flops withheld"
+    # FP64 peak: measured in this very run (DFMA chains on all SMs) with its own clocks record
+    fp = C.c_double(0.0)
+    psam = ClockSampler(local_rank)
+    psam.start()
+    tp0 = time.time()
+    rc_peak = lib.eqlb_measure_fp64_peak(20000, 5, C.byref(fp))
+    pclk = psam.stop(tp0, time.time())
+    if rc_peak == 0 and ncu and not ncu.get("stale") and ncu.get("flop_per_patch"):
         tf = ncu["flop_per_patch"] * m.nnode / (ms_step * 1e-3) / 1e12
-        roof["fp64"] = {"achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
-                        "flop_per_patch": ncu["flop_per_patch"], "source": ncu["capture"],
+        roof["fp64"] = {"achieved": tf, "peak": fp.value, "unit": "TFLOP/s", "frac": tf / fp.value,
+                        "flop_per_patch": ncu["flop_per_patch"], "source": ncu["capture"], "peak_clocks": pclk,
+                        "peak_source": "eqlb_measure_fp64_peak (DFMA chains, this run)",
                         "note": "executed FP64 flop (ncu) / step time; the kernel is FP64/issue bound, see DESIGN.md section 4"}
+    elif rc_peak == 0:
+        roof["fp64"] = {"peak": fp.value, "unit": "TFLOP/s", "peak_clocks": pclk, "peak_source": "eqlb_measure_fp64_peak (DFMA chains, this run)"}
     cpu = None
     if not args.no_cpu and world == 1:  # the CPU baseline is timed at N = 1 only
-        v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress)
+        v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress, neumann=args.neumann)
         cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": "port",
                "sample": f"{procs} processes x crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches each) of the same workload, mean of 3 steps"}
     cfg = workload_config(args)
-    if hx is not None:
-        cfg["halo"] = type(hx).__name__
     line = {
         "metric": "equilibrated patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling_mode(args), "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
         "e2e": {"value": npatch_total / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "halo_check": hcheck, "halo": halo_name,
         # one-time cost per (mesh, BC set), outside the timed region: the reference redoes this work in every call
         # (second handle of the process = the staged host-call one: CUDA context and allocator are warm)
         "setup": {"eqlb_create_ms": 1e3 * hprob.create_seconds, "eqlb_set_bcs_ms": 1e3 * hprob.set_bcs_seconds,
                   "first_handle_ms": 1e3 * (prob.create_seconds + prob.set_bcs_seconds)},
     }
     print(json.dumps(line))
+    if hcheck is not None and not (hcheck <= 1e-12):
+        print(f"[bench] halo_check {hcheck:.3e} > 1e-12", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

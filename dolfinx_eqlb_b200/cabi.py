@@ -178,6 +178,8 @@ def load_library():
     lib.eqlb_halo_destroy.restype = None
     lib.eqlb_launch_count.argtypes = [H]
     lib.eqlb_launch_count.restype = C.c_int64
+    lib.eqlb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, c_double_p]
+    lib.eqlb_measure_fp64_peak.restype = C.c_int
     lib.eqlb_last_error.restype = C.c_char_p
     lib.eqlb_version.restype = C.c_char_p
     _lib = lib

@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .mesh import Mesh, build_topology
+from .mesh import Mesh, build_topology, build_topology_fast
 
 
 # --------------------------------------------------------------------------
@@ -105,6 +105,50 @@ def crossed_strip(n: int, rank: int, world: int) -> tuple[LocalPart, int]:
     own_c = jc.ravel() >= rank * n
     cell_gid = (np.repeat(jc.ravel() * n + ic.ravel(), 4) * 4 + np.tile(np.arange(4), n * nr)).astype(np.int64)
     return LocalPart(m, np.concatenate([own_g, own_c]), node_gid, cell_gid), ngrid_global + n * ny
+
+
+def crossed_rows(n: int, rank: int, world: int, fast: bool = True) -> tuple[LocalPart, int]:
+    """Rank-local part of the STRONG-scaling meshes (BASELINE configs 3-5): the n x n crossed unit
+    square cut into `world` horizontal strips of rows of squares.  Rank r owns the grid-node rows
+    [r0, r1) of its strip (the last rank also the top row y = 1) and the centres of its squares; it
+    holds one extra row of squares below as halo.  Node/cell numbering and geometry are those of
+    `mesh.crossed_unit_square(n)` restricted to the strip (order preserving), boundary ids 1..4 of
+    the global square.  Returns (part, nnode_global)."""
+    rows = [(n * r) // world for r in range(world + 1)]
+    j0 = rows[rank] - (1 if rank > 0 else 0)
+    j1 = rows[rank + 1]
+    nr = j1 - j0
+    ii, jj = np.meshgrid(np.arange(n + 1), np.arange(j0, j1 + 1), indexing="xy")
+    xg = np.stack([ii.ravel() / n, jj.ravel() / n], axis=1)
+    gid_g = (jj.ravel() * (n + 1) + ii.ravel()).astype(np.int64)
+    ic, jc = np.meshgrid(np.arange(n), np.arange(j0, j1), indexing="xy")
+    xc = np.stack([(ic.ravel() + 0.5) / n, (jc.ravel() + 0.5) / n], axis=1)
+    ngrid_global = (n + 1) * (n + 1)
+    gid_c = (ngrid_global + jc.ravel() * n + ic.ravel()).astype(np.int64)
+    x = np.concatenate([xg, xc])
+    node_gid = np.concatenate([gid_g, gid_c])
+    sq_i, sq_jl = ic.ravel(), jc.ravel() - j0
+    v00 = sq_jl * (n + 1) + sq_i
+    v10, v01 = v00 + 1, v00 + (n + 1)
+    v11 = v01 + 1
+    c = (n + 1) * (nr + 1) + sq_jl * n + sq_i
+    tris = np.stack(
+        [np.stack([v00, v10, c], 1), np.stack([v10, v11, c], 1), np.stack([v01, v11, c], 1), np.stack([v00, v01, c], 1)], axis=1
+    ).reshape(-1, 3).astype(np.int32)
+    m = (build_topology_fast if fast else build_topology)(x, tris)
+    # boundary ids: the cut lines (rank > 0: bottom row of the halo squares) are not boundaries
+    mid = 0.5 * (m.x[m.fct_node[m.bfct, 0]] + m.x[m.fct_node[m.bfct, 1]])
+    side = np.zeros(m.bfct.shape[0], dtype=np.int32)
+    side[np.isclose(mid[:, 0], 0.0)] = 1
+    side[np.isclose(mid[:, 1], 0.0)] = 2
+    side[np.isclose(mid[:, 0], 1.0)] = 3
+    side[np.isclose(mid[:, 1], 1.0)] = 4
+    m.bfct_side = side
+    row_g = jj.ravel()
+    own_g = (row_g >= rows[rank]) & ((row_g < rows[rank + 1]) | ((rank == world - 1) & (row_g == n)))
+    own_c = jc.ravel() >= rows[rank]
+    cell_gid = (np.repeat(jc.ravel() * n + ic.ravel(), 4) * 4 + np.tile(np.arange(4), n * nr)).astype(np.int64)
+    return LocalPart(m, np.concatenate([own_g, own_c]), node_gid, cell_gid), ngrid_global + n * n
 
 
 # --------------------------------------------------------------------------

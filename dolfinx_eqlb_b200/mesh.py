@@ -123,6 +123,62 @@ def build_topology(x: np.ndarray, cell_node: np.ndarray) -> Mesh:
     )
 
 
+def build_topology_fast(x: np.ndarray, cell_node: np.ndarray, device=None) -> Mesh:
+    """`build_topology` with the sorts done by torch (on the GPU when one is present): the
+    numpy version needs minutes and > 20 GB for the 4096^2 crossed meshes of BASELINE configs
+    3 and 5 (67 M cells, 100 M facets).  Same arrays, bit for bit (tests/test_mesh.py)."""
+    import torch
+
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    cell_node = np.ascontiguousarray(cell_node, dtype=np.int32)
+    ncell, nnode = cell_node.shape[0], x.shape[0]
+    x3 = np.zeros((nnode, 3))
+    x3[:, : x.shape[1]] = x
+    cn = torch.from_numpy(cell_node).to(device).long()
+    fv = torch.as_tensor(FACET_VERTS, device=device).long()
+    ea, eb = cn[:, fv[:, 0]], cn[:, fv[:, 1]]
+    key = torch.minimum(ea, eb) * nnode + torch.maximum(ea, eb)
+    perms = (ea > eb).to(torch.uint8)
+    del ea, eb
+    ukey, inv = torch.unique(key.reshape(-1), return_inverse=True)
+    del key
+    nfct = int(ukey.shape[0])
+    cell_fct = inv.reshape(ncell, 3).to(torch.int32)
+    del inv
+    fct_node = torch.stack([ukey // nnode, ukey % nnode], dim=1).to(torch.int32)
+    del ukey
+
+    def csr(keys, n, width):
+        # vals = repeat(arange, width) is ascending in input order: a stable sort by key is the lexsort
+        order = torch.sort(keys, stable=True).indices
+        counts = torch.bincount(keys, minlength=n)
+        off = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        torch.cumsum(counts, 0, out=off[1:])
+        return off.to(torch.int32).cpu().numpy(), (order // width).to(torch.int32).cpu().numpy()
+
+    fct_cell_off, fct_cell = csr(cell_fct.reshape(-1).long(), nfct, 3)
+    node_cell_off, node_cell = csr(cn.reshape(-1), nnode, 3)
+    node_fct_off, node_fct = csr(fct_node.reshape(-1).long(), nnode, 2)
+    info = (perms[:, 0].to(torch.int64) | (perms[:, 1].to(torch.int64) << 1) | (perms[:, 2].to(torch.int64) << 2))
+    cell_fct_h = cell_fct.cpu().numpy()
+    fct_node_h = fct_node.cpu().numpy()
+    perms_h = perms.reshape(-1).cpu().numpy()
+    info_h = info.cpu().numpy().astype(np.uint32)
+    del cn, cell_fct, fct_node, perms, info
+    nc_per_f = np.diff(fct_cell_off)
+    bfct = np.nonzero(nc_per_f == 1)[0].astype(np.int32)
+    mid = 0.5 * (x3[fct_node_h[bfct, 0]] + x3[fct_node_h[bfct, 1]])
+    side = np.zeros(bfct.shape[0], dtype=np.int32)
+    side[np.isclose(mid[:, 0], 0.0)] = 1
+    side[np.isclose(mid[:, 1], 0.0)] = 2
+    side[np.isclose(mid[:, 0], 1.0)] = 3
+    side[np.isclose(mid[:, 1], 1.0)] = 4
+    return Mesh(x=x3, cell_node=cell_node, cell_fct=cell_fct_h, fct_node=fct_node_h, fct_cell_off=fct_cell_off,
+                fct_cell=fct_cell, node_cell_off=node_cell_off, node_cell=node_cell, node_fct_off=node_fct_off,
+                node_fct=node_fct, fct_perms=np.ascontiguousarray(perms_h), cell_perm_info=info_h, bfct=bfct, bfct_side=side)
+
+
 def _scramble(cell_node, rng):
     """Random permutation of the local vertex order of every cell: produces
     reversed facets and negative Jacobians (stand-in for the reference's gmsh
@@ -131,7 +187,7 @@ def _scramble(cell_node, rng):
     return np.take_along_axis(cell_node, perm, axis=1)
 
 
-def crossed_unit_square(n: int, scramble_seed: int | None = None, perturb: float = 0.0, seed: int = 7) -> Mesh:
+def crossed_unit_square(n: int, scramble_seed: int | None = None, perturb: float = 0.0, seed: int = 7, fast: bool = False) -> Mesh:
     """n x n squares, each split into 4 triangles by both diagonals
     (`DiagonalType.crossed`, the reference's benchmark mesh `perftest.py:62-63`).
 
@@ -166,7 +222,7 @@ def crossed_unit_square(n: int, scramble_seed: int | None = None, perturb: float
     ).reshape(-1, 3)
     if scramble_seed is not None:
         tris = _scramble(tris, np.random.default_rng(scramble_seed))
-    return build_topology(x, tris)
+    return (build_topology_fast if fast else build_topology)(x, tris)
 
 
 def random_diagonal_square(n: int, seed: int = 3, scramble_seed: int | None = None, perturb: float = 0.0) -> Mesh:

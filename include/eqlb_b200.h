@@ -222,6 +222,11 @@ int eqlb_unpin_host(void* ptr);
 /* number of kernel launches issued by this handle so far (bench "gpu_launches") */
 int64_t eqlb_launch_count(eqlb_handle* h);
 
+/* Measurement aid for the FP64 roofline (not on the hot path): register-resident DFMA chains
+ * on every SM of the current device for `iters` iterations, best of `reps` launches timed with
+ * CUDA events; returns TFLOP/s (2 flop per FMA) in *tflops. */
+int eqlb_measure_fp64_peak(int iters, int reps, double* tflops);
+
 const char* eqlb_last_error(void);
 const char* eqlb_version(void);
 

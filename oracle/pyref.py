@@ -75,6 +75,11 @@ def lib():
             C.POINTER(EqlbMesh), C.POINTER(RefElement), C.c_int, c_int8_p, C.c_int,
             c_int32_p, c_int32_p, c_int32_p, c_int8_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
         ]
+        L.ref_ev_run.restype = C.c_int
+        L.ref_ev_run.argtypes = [
+            C.POINTER(EqlbMesh), C.POINTER(RefElement), C.c_int, c_int8_p, C.POINTER(c_double_p),
+            C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p),
+        ]
         _lib = L
     return _lib
 
@@ -184,3 +189,21 @@ def ev_patch_maps(mesh, tables, bc, node):
     _check(rc)
     out["ncells"] = int(nc[0])
     return out
+
+
+def ev_run(mesh, tables, bc, G, F, sigma0=None):
+    """`reconstruct_fluxes_minimisation` of the reference (ev::reconstruction with its own patch
+    assembly, lifting, dense partial-pivot LU and scatter) -> conforming hierarchic-RT vectors."""
+    pm, pe = PackedMesh(mesh, tables.ndg), PackedElement(tables.k, tables.p, continuous=True)
+    nrhs = bc.nrhs
+    G = [np.ascontiguousarray(g, dtype=np.float64) for g in G]
+    F = [np.ascontiguousarray(f, dtype=np.float64) for f in F]
+    k = tables.k
+    n = mesh.nfct * k + mesh.ncell * (k * k - k)
+    sig = [np.zeros(n) if sigma0 is None else np.array(sigma0[i], dtype=np.float64) for i in range(nrhs)]
+    rc = lib().ref_ev_run(
+        C.byref(pm.struct), C.byref(pe.struct), nrhs, _i8(bc.facet_type), ptr_array(bc.bflux), ptr_array(G), ptr_array(F),
+        ptr_array(sig),
+    )
+    _check(rc)
+    return sig

@@ -11,6 +11,7 @@
 #include <dolfinx_eqlb/base/BoundaryData.hpp>
 #include <dolfinx_eqlb/base/FluxBC.hpp>
 #include <dolfinx_eqlb/ev/Patch.hpp>
+#include <dolfinx_eqlb/ev/reconstruction.hpp>
 #include <dolfinx_eqlb/se/reconstruction.hpp>
 
 #include "../include/eqlb_b200.h"
@@ -504,6 +505,337 @@ int ref_ev_patch_maps(const eqlb_mesh* mesh, const ref_element* elmt, int nrhs, 
           list_patch[i] = lp[i];
           list_global[i] = lg[i];
         }
+      });
+}
+}
+
+namespace
+{
+/// The three fixed forms of FluxEqlbEV (`python/dolfinx_eqlb/eqlb/FluxEqlbEV.py:116-133`) as cell kernels
+/// with the FFCx `tabulate_tensor` signature.  FFCx itself is third party and absent; these are the
+/// integrals as written in the UFL forms, evaluated by quadrature of the Piola-mapped basis on the
+/// (affine) cell, WITHOUT DOF transformations (the reference applies those itself, `ev/assembly.hpp:185-198`):
+///   a      = (sig, v) - (r, div v) + (div sig, q)                  A[test i][trial j], mixed RT_k x DG_(k-1)
+///   l_pen  = (1, q)
+///   l      = (hat G, v) + (hat f + grad(hat) . G, q)               coefficients packed as [G (ndg x 2) | f (ndg) | hat (3)]
+struct EvForms
+{
+  int nrt, ndg, nd, nq;
+  std::vector<double> w, rt, rtdiv, dg, hat; // rt [q][i][2], rtdiv [q][i], dg [q][c], hat [q][3]
+
+  EvForms(const basix::FiniteElement& el_rt, const basix::FiniteElement& el_dg, int k)
+  {
+    nrt = el_rt.dim();
+    ndg = el_dg.dim();
+    nd = nrt + ndg;
+    auto quad = basix::quadrature::make_quadrature(basix::cell::type::triangle, 2 * k + 1);
+    const std::vector<double>& pts = quad[0];
+    w = quad[1];
+    nq = (int)w.size();
+    std::vector<double> t((size_t)3 * nq * nrt * 2);
+    el_rt.tabulate(1, pts, {(size_t)nq, 2}, t);
+    rt.assign(t.begin(), t.begin() + (size_t)nq * nrt * 2);
+    rtdiv.resize((size_t)nq * nrt);
+    const size_t plane = (size_t)nq * nrt * 2;
+    for (int q = 0; q < nq; ++q)
+      for (int i = 0; i < nrt; ++i)
+        rtdiv[(size_t)q * nrt + i] = t[plane + ((size_t)q * nrt + i) * 2] + t[2 * plane + ((size_t)q * nrt + i) * 2 + 1];
+    dg.resize((size_t)nq * ndg);
+    el_dg.tabulate(0, pts, {(size_t)nq, 2}, dg);
+    hat.resize((size_t)nq * 3);
+    for (int q = 0; q < nq; ++q)
+    {
+      hat[3 * q] = 1.0 - pts[2 * q] - pts[2 * q + 1];
+      hat[3 * q + 1] = pts[2 * q];
+      hat[3 * q + 2] = pts[2 * q + 1];
+    }
+  }
+
+  static double jac(const double* x, double J[4], double K[4])
+  {
+    J[0] = x[3] - x[0];
+    J[1] = x[6] - x[0];
+    J[2] = x[4] - x[1];
+    J[3] = x[7] - x[1];
+    const double det = J[0] * J[3] - J[1] * J[2];
+    K[0] = J[3] / det;
+    K[1] = -J[1] / det;
+    K[2] = -J[2] / det;
+    K[3] = J[0] / det;
+    return det;
+  }
+
+  void kernel_a(double* A, const double* x) const
+  {
+    double J[4], K[4];
+    const double det = jac(x, J, K);
+    std::vector<double> phi((size_t)nrt * 2);
+    for (int q = 0; q < nq; ++q)
+    {
+      const double dv = w[q] * std::fabs(det);
+      for (int i = 0; i < nrt; ++i)
+      {
+        const double r0 = rt[((size_t)q * nrt + i) * 2], r1 = rt[((size_t)q * nrt + i) * 2 + 1];
+        phi[2 * i] = (J[0] * r0 + J[1] * r1) / det;
+        phi[2 * i + 1] = (J[2] * r0 + J[3] * r1) / det;
+      }
+      for (int i = 0; i < nrt; ++i)
+      {
+        const double divi = rtdiv[(size_t)q * nrt + i] / det;
+        for (int j = 0; j < nrt; ++j)
+          A[i * nd + j] += dv * (phi[2 * i] * phi[2 * j] + phi[2 * i + 1] * phi[2 * j + 1]);
+        for (int c = 0; c < ndg; ++c)
+        {
+          const double psi = dg[(size_t)q * ndg + c];
+          A[i * nd + nrt + c] -= dv * psi * divi;
+          A[(nrt + c) * nd + i] += dv * divi * psi;
+        }
+      }
+    }
+  }
+
+  void kernel_lpen(double* P, const double* x) const
+  {
+    double J[4], K[4];
+    const double det = jac(x, J, K);
+    for (int q = 0; q < nq; ++q)
+      for (int c = 0; c < ndg; ++c)
+        P[c] += w[q] * std::fabs(det) * dg[(size_t)q * ndg + c];
+  }
+
+  void kernel_l(double* L, const double* cf, const double* x) const
+  {
+    double J[4], K[4];
+    const double det = jac(x, J, K);
+    const double* G = cf;
+    const double* f = cf + 2 * ndg;
+    const double* h = cf + 3 * ndg;
+    // grad(hat) = K^T grad_ref(hat)
+    const double gr[3][2] = {{-1, -1}, {1, 0}, {0, 1}};
+    double gh[2] = {0, 0};
+    for (int n = 0; n < 3; ++n)
+    {
+      gh[0] += h[n] * (K[0] * gr[n][0] + K[2] * gr[n][1]);
+      gh[1] += h[n] * (K[1] * gr[n][0] + K[3] * gr[n][1]);
+    }
+    for (int q = 0; q < nq; ++q)
+    {
+      const double dv = w[q] * std::fabs(det);
+      double hq = 0, Gq[2] = {0, 0}, fq = 0;
+      for (int n = 0; n < 3; ++n)
+        hq += h[n] * hat[3 * q + n];
+      for (int c = 0; c < ndg; ++c)
+      {
+        const double psi = dg[(size_t)q * ndg + c];
+        Gq[0] += G[2 * c] * psi;
+        Gq[1] += G[2 * c + 1] * psi;
+        fq += f[c] * psi;
+      }
+      for (int i = 0; i < nrt; ++i)
+      {
+        const double r0 = rt[((size_t)q * nrt + i) * 2], r1 = rt[((size_t)q * nrt + i) * 2 + 1];
+        const double p0 = (J[0] * r0 + J[1] * r1) / det, p1 = (J[2] * r0 + J[3] * r1) / det;
+        L[i] += dv * hq * (Gq[0] * p0 + Gq[1] * p1);
+      }
+      const double s = hq * fq + gh[0] * Gq[0] + gh[1] * Gq[1];
+      for (int c = 0; c < ndg; ++c)
+        L[nrt + c] += dv * s * dg[(size_t)q * ndg + c];
+    }
+  }
+};
+
+/// DOLFINx' DOF transformations of the conforming hierarchic RT element on reflected facets
+/// (`topology().get_facet_permutations()` bit): facet functionals int v.n s^j ds with s -> 1-s and
+/// n -> -n give c_glob = R c_loc, R[j][i] = (-1)^(i+1) binom(j, i) (an involution: the matrix of
+/// `se/KernelData.cpp:55-64`), hence phi_glob = M phi_loc with M = R^T on the facet block.
+struct RtTransform
+{
+  int k, nrt;
+  std::vector<double> R; // [k][k]
+  const std::uint8_t* perms;
+
+  RtTransform(int k_, int nrt_, const std::uint8_t* p) : k(k_), nrt(nrt_), R((size_t)k_ * k_, 0.0), perms(p)
+  {
+    for (int j = 0; j < k; ++j)
+    {
+      long b = 1;
+      for (int i = 0; i <= j; ++i)
+      {
+        R[j * k + i] = ((i % 2) == 0) ? -(double)b : (double)b;
+        b = b * (j - i) / (i + 1);
+      }
+    }
+  }
+  /// data (ndofs x bs) <- Mb data, Mb = R^T (transpose = false) or R (transpose = true) on reflected facet blocks
+  void pre(const std::span<double>& data, std::int32_t cell, int bs, bool use_R) const
+  {
+    std::vector<double> tmp((size_t)k * bs);
+    for (int f = 0; f < 3; ++f)
+      if (perms[3 * cell + f])
+      {
+        for (int i = 0; i < k; ++i)
+          for (int b = 0; b < bs; ++b)
+          {
+            double s = 0;
+            for (int j = 0; j < k; ++j)
+              s += (use_R ? R[i * k + j] : R[j * k + i]) * data[(size_t)(f * k + j) * bs + b];
+            tmp[(size_t)i * bs + b] = s;
+          }
+        for (int i = 0; i < k; ++i)
+          for (int b = 0; b < bs; ++b)
+            data[(size_t)(f * k + i) * bs + b] = tmp[(size_t)i * bs + b];
+      }
+  }
+  /// data (bs x ndofs, row length nd) <- data M^T
+  void post_t(const std::span<double>& data, std::int32_t cell, int bs, int nd) const
+  {
+    std::vector<double> tmp(k);
+    for (int f = 0; f < 3; ++f)
+      if (perms[3 * cell + f])
+        for (int b = 0; b < bs; ++b)
+        {
+          for (int i = 0; i < k; ++i)
+          {
+            double s = 0;
+            for (int j = 0; j < k; ++j)
+              s += data[(size_t)b * nd + f * k + j] * R[j * k + i]; // (data M^T)[i] = sum_j data[j] M[i][j], M = R^T
+            tmp[i] = s;
+          }
+          for (int i = 0; i < k; ++i)
+            data[(size_t)b * nd + f * k + i] = tmp[i];
+        }
+  }
+};
+} // namespace
+
+extern "C"
+{
+/// `reconstruct_fluxes_minimisation` (wrappers.cpp:85-95) -> ev::reconstruction (ev/reconstruction.hpp:64-177):
+/// the reference's patch loop, ev::Patch, assemble_tangents, apply_lifting, dense partial-pivot LU and the
+/// += scatter run unchanged; forms and DOF transformations as described above.  sigma: conforming
+/// hierarchic-RT vectors [nfct*k + ncell*(k*k-k)], accumulated; bflux as for ref_se_run (DRT layout,
+/// cell-local moments).  Arguments as oracle_ev_run.
+int ref_ev_run(const eqlb_mesh* mesh, const ref_element* elmt, int nrhs, const int8_t* facet_type, const double* const* bflux,
+               const double* const* G, const double* const* F, double* const* sigma)
+{
+  return guarded(
+      [&]
+      {
+        auto msh = make_mesh(mesh);
+        const int k = elmt->k, nrt = elmt->nrt;
+        basix::FiniteElement rt = make_rt(elmt, false);
+        basix::FiniteElement dg
+            = basix::element::create_lagrange(basix::cell::type::triangle, elmt->p, basix::element::lagrange_variant::equispaced, true);
+        basix::FiniteElement p1
+            = basix::element::create_lagrange(basix::cell::type::triangle, 1, basix::element::lagrange_variant::equispaced, false);
+        const int ndg = dg.dim(), nel = nrt + ndg;
+        const std::int32_t nc = mesh->ncell;
+        const std::int32_t nflux = mesh->nfct * k + nc * (nrt - 3 * k), nmixed = nflux + nc * ndg;
+        std::vector<std::int32_t> mixed((size_t)nc * nel), flux((size_t)nc * nrt);
+        for (std::int32_t c = 0; c < nc; ++c)
+          for (int l = 0; l < nel; ++l)
+          {
+            std::int32_t g;
+            if (l < 3 * k)
+              g = mesh->cell_fct[3 * c + l / k] * k + l % k;
+            else if (l < nrt)
+              g = mesh->nfct * k + c * (nrt - 3 * k) + (l - 3 * k);
+            else
+              g = nflux + c * ndg + (l - nrt);
+            mixed[(size_t)c * nel + l] = g;
+            if (l < nrt)
+              flux[(size_t)c * nrt + l] = g;
+          }
+        auto trafo = std::make_shared<RtTransform>(k, nrt, mesh->fct_perms);
+        auto install = [&](fem::FiniteElement& e, int nd)
+        {
+          e.set_transformations(
+              [trafo](const std::span<double>& d, const std::span<const std::uint32_t>&, std::int32_t c, int bs)
+              { trafo->pre(d, c, bs, false); },
+              [trafo, nd](const std::span<double>& d, const std::span<const std::uint32_t>&, std::int32_t c, int bs)
+              { trafo->post_t(d, c, bs, nd); },
+              [trafo](const std::span<double>& d, const std::span<const std::uint32_t>&, std::int32_t c, int bs)
+              { trafo->pre(d, c, bs, true); });
+        };
+        auto el_mixed = std::make_shared<fem::FiniteElement>(rt, 1);
+        el_mixed->set_space_dimension(nel);
+        install(*el_mixed, nel);
+        auto el_flux = std::make_shared<fem::FiniteElement>(rt, 1);
+        install(*el_flux, nrt);
+        fem::ElementDofLayout layout(rt.entity_dofs());
+        auto V = std::make_shared<fem::FunctionSpace>(
+            msh, el_mixed, std::make_shared<const fem::DofMap>(AL::regular(mixed.data(), nc, nel), nmixed, 1, layout));
+        // V.sub(0): the flux sub-space keeps the parent's numbering and index map (`FluxEqlbEV.py:158`)
+        auto V0 = std::make_shared<fem::FunctionSpace>(
+            msh, el_flux, std::make_shared<const fem::DofMap>(AL::regular(flux.data(), nc, nrt), nmixed, 1, layout));
+        V->add_sub(V0);
+        auto V_flux = std::make_shared<fem::FunctionSpace>(
+            msh, el_flux, std::make_shared<const fem::DofMap>(AL::regular(flux.data(), nc, nrt), nflux, 1, layout));
+        auto V_dg2 = std::make_shared<fem::FunctionSpace>(
+            msh, std::make_shared<const fem::FiniteElement>(dg, 2),
+            std::make_shared<const fem::DofMap>(AL::regular(mesh->dg_dofmap, nc, ndg), nc * ndg, 2, fem::ElementDofLayout(dg.entity_dofs())));
+        auto V_dg = std::make_shared<fem::FunctionSpace>(
+            msh, std::make_shared<const fem::FiniteElement>(dg, 1),
+            std::make_shared<const fem::DofMap>(AL::regular(mesh->dg_dofmap, nc, ndg), nc * ndg, 1, fem::ElementDofLayout(dg.entity_dofs())));
+        auto V_hat = std::make_shared<fem::FunctionSpace>(
+            msh, std::make_shared<const fem::FiniteElement>(p1, 1),
+            std::make_shared<const fem::DofMap>(AL::regular(mesh->cell_node, nc, 3), mesh->nnode, 1, fem::ElementDofLayout(p1.entity_dofs())));
+
+        // boundary data: facet types + boundary function in the global orientation (c_glob = R c_loc)
+        std::vector<std::vector<double>> bvals(nrhs, std::vector<double>(nmixed, 0.0));
+        std::vector<std::shared_ptr<fem::Function<double>>> bfuncs;
+        std::vector<std::vector<std::shared_ptr<eqlb::base::FluxBC<double>>>> no_bcs(nrhs);
+        std::vector<std::vector<std::int32_t>> fct_prime(nrhs);
+        for (int r = 0; r < nrhs; ++r)
+        {
+          for (int f = 0; f < mesh->nfct; ++f)
+          {
+            const int8_t ft = facet_type[(size_t)r * mesh->nfct + f];
+            if (ft == eqlb::base::PatchFacetType::essnt_primal)
+              fct_prime[r].push_back(f);
+            if (ft == eqlb::base::PatchFacetType::essnt_dual && bflux && bflux[r])
+            {
+              const std::int32_t c = mesh->fct_cell[mesh->fct_cell_off[f]];
+              int fl = 0;
+              for (int j = 0; j < 3; ++j)
+                if (mesh->cell_fct[3 * c + j] == f)
+                  fl = j;
+              std::vector<double> cl(nrt, 0.0);
+              for (int j = 0; j < k; ++j)
+                cl[fl * k + j] = bflux[r][(size_t)c * nrt + fl * k + j];
+              trafo->pre(std::span<double>(cl), c, 1, true);
+              for (int j = 0; j < k; ++j)
+                bvals[r][f * k + j] = cl[fl * k + j];
+            }
+          }
+          bfuncs.push_back(std::make_shared<fem::Function<double>>(V, std::make_shared<la::Vector<double>>(bvals[r].data(), nmixed)));
+        }
+        std::shared_ptr<eqlb::base::BoundaryData<double>> bd = std::make_shared<InjectedBoundaryData>(
+            no_bcs, bfuncs, V0, std::max(2 * (k - 1), 0), fct_prime, false, mesh, nrhs, facet_type, nullptr, nullptr);
+
+        // forms
+        auto forms = std::make_shared<EvForms>(rt, dg, k);
+        using kern_t = fem::Form<double>::kernel_t;
+        kern_t ka = [forms](double* A, const double*, const double*, const double* x, const int*, const std::uint8_t*) { forms->kernel_a(A, x); };
+        kern_t kp = [forms](double* P, const double*, const double*, const double* x, const int*, const std::uint8_t*) { forms->kernel_lpen(P, x); };
+        kern_t kl = [forms](double* L, const double* w, const double*, const double* x, const int*, const std::uint8_t*) { forms->kernel_l(L, w, x); };
+        fem::Form<double> a({V, V}, ka, {}, {}, msh);
+        fem::Form<double> l_pen({V_dg}, kp, {}, {}, msh);
+        std::vector<double> hat0(mesh->nnode, 0.0);
+        auto hat = std::make_shared<fem::Function<double>>(V_hat, std::make_shared<la::Vector<double>>(hat0.data(), hat0.size()));
+        hat->name = "hat";
+        std::vector<std::shared_ptr<const fem::Form<double>>> l;
+        std::vector<std::shared_ptr<fem::Function<double>>> flux_hdiv;
+        for (int r = 0; r < nrhs; ++r)
+        {
+          auto Gf = std::make_shared<fem::Function<double>>(V_dg2, std::make_shared<la::Vector<double>>(const_cast<double*>(G[r]), (size_t)nc * ndg * 2));
+          auto Ff = std::make_shared<fem::Function<double>>(V_dg, std::make_shared<la::Vector<double>>(const_cast<double*>(F[r]), (size_t)nc * ndg));
+          std::vector<std::shared_ptr<const fem::Function<double>>> cf{Gf, Ff, hat};
+          l.push_back(std::make_shared<const fem::Form<double>>(std::vector<std::shared_ptr<const fem::FunctionSpace>>{V}, kl, cf,
+                                                                std::vector<std::shared_ptr<const fem::Constant<double>>>{}, msh));
+          flux_hdiv.push_back(std::make_shared<fem::Function<double>>(V_flux, std::make_shared<la::Vector<double>>(sigma[r], nflux)));
+        }
+        eqlb::ev::reconstruction<double>(a, l_pen, l, flux_hdiv, bd);
       });
 }
 }

@@ -18,6 +18,7 @@
 #include <span>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -233,6 +234,15 @@ private:
 
 namespace fem
 {
+namespace impl
+{
+template <typename T>
+using scalar_value_type_t = T;
+}
+/// form kernel signature (FFCx `tabulate_tensor`)
+template <class U, class T>
+concept FEkernel = std::is_invocable_v<U, T*, const T*, const T*, const impl::scalar_value_type_t<T>*, const int*, const std::uint8_t*>;
+
 enum class IntegralType : std::int8_t
 {
   cell = 0,

@@ -4,9 +4,9 @@ SE and stress fixtures (`se_*`, `stress_*`) are OUTPUTS OF THE REFERENCE ITSELF:
 sources compiled unchanged against stand-in headers (`oracle/_ref/libeqlb_ref.so`, recipe
 `make -C oracle ref`, needs /root/reference) run on seeded inputs on the reference's own
 fixture sizes (2x2 / 5x5 crossed unit squares, test_fluxeqlb_conditions.py:47-49); the
-files carry `source = "reference"`.  EV fixtures (`ev_*`) come from the oracle (the EV
-numerics need FFCx-generated kernels, which cannot be produced offline; the EV integer
-maps are pinned against the reference's ev::Patch in tests/test_ref_pinning.py).  Every
+files carry `source = "reference"`.  EV fixtures (`ev_*`) come from the reference's
+ev::reconstruction in the same library (its patch loop, assembly, lifting, LU and scatter;
+the three fixed FFCx forms and the DOF transformations are restated in oracle/ref_driver.cpp).  Every
 vector is accepted only if the reference's acceptance invariants hold.
 Run from the repo root (build container):  python tests/golden/make_golden.py"""
 
@@ -70,7 +70,7 @@ def main():
                 assert fm.check_divergence(m, case.T, sig[r], case.G[r], case.F[r]) < 1e-12
                 assert fm.check_jump(m, case.T, sig[r], case.G[r]) < 1e-12
         else:
-            sig = po.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
+            sig = pr.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
             for r in range(case.nrhs):
                 s = fm.conforming_to_drt(m, case.T, sig[r])
                 z = np.zeros_like(case.G[r])
@@ -79,7 +79,7 @@ def main():
         maps = (pr if path == "se" else po).se_patch_maps(m, case.T, case.oracle_bc())
         np.savez_compressed(
             os.path.join(out, name + ".npz"), G=np.array(case.G), F=np.array(case.F), sigma=np.array(sig),
-            source=np.array("reference" if path == "se" else "oracle"),
+            source=np.array("reference"),
             cells=maps["cells"], fcts=maps["fcts"], type=maps["type"], fcts_local=maps["fcts_local"],
             reversed=maps["reversed"], cell_node=m.cell_node, x=m.x,
         )

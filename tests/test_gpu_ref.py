@@ -76,3 +76,18 @@ def test_ev_dofmaps_vs_reference(kind, n, scramble, k):
         assert got["ncells"][z] == ref["ncells"]
         for key in ("cells", "fcts", "inodes_local", "dofs_elmt", "dofs_patch", "dofs_global", "list_patch", "list_global"):
             assert np.array_equal(got[key][z], ref[key]), (z, key)
+
+
+@pytest.mark.parametrize("kind,n,scramble,hom", [("crossed", 4, 3, True), ("randdiag", 6, 2, True), ("crossed", 5, None, False)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("nsets", [[[]], [[1, 4], [1, 3]]])
+def test_ev_flux_vs_reference(kind, n, scramble, hom, k, nsets):
+    """EV (headline path): CUDA null-space kernels vs the reference's dense-KKT ev::reconstruction"""
+    m = make_mesh(kind, n, scramble, perturb=0.25)
+    case = PoissonCase(m, k, nsets, seed=1, hom=hom)
+    ref = pr.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    eq = eqlb.FluxEqlbEV(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    eq.equilibrate_fluxes()
+    for r in range(case.nrhs):
+        assert rel_err(eq.list_flux[r], ref[r]) < RTOL

@@ -40,3 +40,37 @@ def test_crossed_counts():
     nc = np.diff(m.node_cell_off)
     assert set(nc[(n + 1) ** 2 :]) == {4}
     assert nc.max() == 8
+
+
+def test_fast_topology_builder_is_bit_identical():
+    """torch-sorted builder (used for the 2048^2 / 4096^2 benchmark meshes) == numpy builder"""
+    for n, scr in [(4, None), (6, 3)]:
+        a = ms.crossed_unit_square(n, scr)
+        b = ms.crossed_unit_square(n, scr, fast=True)
+        for f in a.__dataclass_fields__:
+            x, y = getattr(a, f), getattr(b, f)
+            assert x.dtype == y.dtype and np.array_equal(x, y), f
+
+
+def test_strong_scaling_strips_tile_the_global_mesh():
+    """`dist.crossed_rows`: every rank's local mesh is the restriction of crossed_unit_square(n)
+    (same cells, same geometry, order preserving), every vertex is owned exactly once."""
+    from dolfinx_eqlb_b200 import dist as dd
+
+    n, world = 12, 3
+    g = ms.crossed_unit_square(n)
+    owned = np.zeros(g.nnode, dtype=np.int32)
+    for r in range(world):
+        part, nn = dd.crossed_rows(n, r, world, fast=False)
+        assert nn == g.nnode
+        lm = part.mesh
+        assert np.array_equal(part.node_gid[lm.cell_node], g.cell_node[part.cell_gid])
+        assert np.abs(lm.x - g.x[part.node_gid]).max() < 1e-15
+        np.add.at(owned, part.node_gid[part.node_owned.astype(bool)], 1)
+        # boundary ids of the global square only (cut lines are not boundaries)
+        gl = part.node_gid[lm.fct_node[lm.bfct]]
+        gkey = g.fct_node[g.bfct, 0].astype(np.int64) * g.nnode + g.fct_node[g.bfct, 1]
+        side_of = dict(zip(gkey.tolist(), g.bfct_side.tolist()))
+        for (a, b), s in zip(gl, lm.bfct_side):
+            assert side_of.get(int(a) * g.nnode + int(b), 0) == s
+    assert (owned == 1).all()

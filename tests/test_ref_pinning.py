@@ -145,3 +145,29 @@ def test_facet_orientation_convention_is_pinned_by_the_reference_invariants():
     assert fm.check_divergence(m, case.T, good, case.G[0], case.F[0]) < 1e-12
     assert fm.check_jump(m, case.T, good, case.G[0]) < 1e-11
     assert fm.check_divergence(m, case.T, bad, case.G[0], case.F[0]) > 1e-3
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,n,scramble,hom", [("crossed", 2, None, True), ("crossed", 4, 3, True), ("randdiag", 5, 2, True),
+                                                 ("crossed", 4, None, False)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("nsets", [[[]], [[1, 4], [1, 3]]])
+def test_oracle_matches_reference_ev(kind, n, scramble, hom, k, nsets):
+    """EV flux DOFs: oracle vs the reference's ev::reconstruction (its own patch loop, assemble_tangents,
+    apply_lifting, dense partial-pivot LU, scatter; fixed forms and DOF transformations restated in
+    oracle/ref_driver.cpp).  Inhomogeneous Neumann data only on meshes without reflected facets: the
+    reference does not transform patch BCs to the global facet orientation (`base/BoundaryData.cpp:736-743`,
+    DESIGN.md section 6) and tests homogeneous data only (`test_fluxeqlb_conditions.py:147,156`)."""
+    from oracle import pyoracle as po
+
+    m = make_mesh(kind, n, scramble, perturb=0.25)
+    case = PoissonCase(m, k, nsets, seed=1, hom=hom)
+    bc = case.oracle_bc()
+    a, b = po.ev_run(m, case.T, bc, case.G, case.F), pr.ev_run(m, case.T, bc, case.G, case.F)
+    for x, y in zip(a, b):
+        assert np.abs(x - y).max() < 1e-11 * np.abs(y).max()
+    # the reference's own EV output: divergence + conformity invariants
+    for r in range(case.nrhs):
+        s = fm.conforming_to_drt(m, case.T, b[r])
+        z = np.zeros_like(case.G[r])
+        assert fm.check_jump(m, case.T, s, z) < 1e-11

@@ -209,10 +209,11 @@ def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue, stress=False
     from oracle import pyoracle as po
     from dolfinx_eqlb_b200 import eqlb
 
+    impl = cpu_impl()[1]  # the reference's own compiled sources (oracle/_ref) when present, else the oracle port
     m, T, G, F, bfct, bcs = build_case(n, k, nrhs, neumann, fast=False)
     bd = eqlb.boundarydata(bcs, m, T, bfct, stress)
     bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
-    run = (lambda: po.se_run(m, T, bc, G, F, stress=stress)) if path == "se" else (lambda: po.ev_run(m, T, bc, G, F))
+    run = (lambda: impl.se_run(m, T, bc, G, F, stress=stress)) if path == "se" else (lambda: impl.ev_run(m, T, bc, G, F))
     for _ in range(warmup):
         run()
     barrier.wait()
@@ -222,6 +223,20 @@ def _oracle_worker(path, n, k, nrhs, warmup, steps, barrier, queue, stress=False
         run()
         dts.append(time.perf_counter() - t0)
     queue.put((m.nnode, dts))
+
+
+def cpu_impl():
+    """("reference", pyref) when oracle/_ref/libeqlb_ref.so (the reference's own sources compiled unchanged
+    against stand-in headers) is available, else ("port", pyoracle)."""
+    from oracle import pyoracle as po, pyref as pr
+
+    if os.environ.get("EQLB_CPU_IMPL", "") != "port" and pr.available():
+        try:
+            pr.lib()
+            return "reference", pr
+        except Exception:
+            pass
+    return "port", po
 
 
 def host_cores():
@@ -254,8 +269,9 @@ def time_oracle(path, n, k, nrhs, steps, warmup=0, procs=None, stress=False, neu
 
 
 def reference_arm(args):
-    """`--impl reference`: the reference's CPU algorithm (oracle port; the reference
-    itself cannot be built here - SURVEY 8c) on all host cores of the box."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores of the box:
+    `oracle/_ref` (its sources compiled unchanged against stand-in DOLFINx/Basix/Eigen headers) when the
+    library travelled with the snapshot, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -271,7 +287,7 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": scaling_mode(args), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": procs, "kind": cpu_impl()[0], "sample": sample},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": total,
     }
@@ -661,7 +677,7 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:  # the CPU baseline is timed at N = 1 only
         v, npatch_s, dt, procs = time_oracle(args.path, args.cpu_n, k, nrhs, 3, 1, stress=args.stress, neumann=args.neumann)
-        cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": "port",
+        cpu = {"value": v, "unit": "patches/s", "cores": procs, "kind": cpu_impl()[0],
                "sample": f"{procs} processes x crossed {args.cpu_n}x{args.cpu_n} ({npatch_s} patches each) of the same workload, mean of 3 steps"}
     cfg = workload_config(args)
     line = {

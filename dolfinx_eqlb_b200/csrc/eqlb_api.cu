@@ -238,6 +238,125 @@ eqlb_handle::~eqlb_handle()
     cudaStreamDestroy(s_d2h);
 }
 
+// Shared tail of eqlb_set_bcs / eqlb_set_bcs_poly: grouping of 2-cell traction patches (host, needs the
+// facet types and node markers on the host), colouring, record buffers, device patch builder.
+static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* node_on_stress_bnd, bool upload_node_markers,
+                       StageTimer& tm)
+{
+    if (node_on_stress_bnd)
+    {
+      if (upload_node_markers)
+        h->d_node_on_bnd.upload(node_on_stress_bnd, h->nnode);
+      // grouped boundary patches (se/reconstruction.hpp:170-234, k == 2 only): 2-cell
+      // patches on a pure traction boundary are solved together with the adjacent
+      // patch, which then imposes weak symmetry on the accumulated global stress
+      h->h_grouped.assign(h->nnode, 0);
+      h->h_group_off.clear();
+      std::vector<int32_t> gorder;
+      if ((h->flags & EQLB_FLAG_STRESS) && h->k == 2)
+      {
+        auto ncells_of = [&](int z) { return h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]; };
+        std::vector<uint8_t> perform(h->nnode, 1);
+        for (int z = 0; z < h->nnode; ++z)
+        {
+          if (!(node_on_stress_bnd[z] && perform[z] && h->h_owned[z]) || ncells_of(z) != 2)
+            continue;
+          // adjacent_internal_patch (se/Patch.cpp:761-784)
+          int inner = -1;
+          for (int i = h->h_node_fct_off[z]; i < h->h_node_fct_off[z + 1]; ++i)
+          {
+            const int32_t fct = h->h_node_fct[i];
+            if (facet_type[fct] == EQLB_FCT_INTERNAL)
+            {
+              inner = (h->h_fct_node[2 * fct] == z) ? h->h_fct_node[2 * fct + 1] : h->h_fct_node[2 * fct];
+              break;
+            }
+          }
+          // group_boundary_patches (se/Patch.cpp:60-104)
+          std::vector<int32_t> grouped{inner};
+          for (int i = h->h_node_cell_off[inner]; i < h->h_node_cell_off[inner + 1]; ++i)
+            for (int j = 0; j < 3; ++j)
+            {
+              const int32_t pnt = h->h_cell_node[3 * (size_t)h->h_node_cell[i] + j];
+              if (node_on_stress_bnd[pnt] && std::find(grouped.begin(), grouped.end(), pnt) == grouped.end()
+                  && ncells_of(pnt) == 2)
+                grouped.push_back(pnt);
+            }
+          if (grouped.size() < 2)
+            continue;
+          if (h->h_group_off.empty())
+            h->h_group_off.push_back(0);
+          for (int32_t q : grouped)
+          {
+            if (!perform[q] || !h->h_owned[q])
+              throw EqlbError(EQLB_ERR_INPUT,
+                              "Incompatible mesh! To many patches with 2 cells on neumann boundary.");
+            perform[q] = 0;
+            h->h_grouped[q] = 1;
+            gorder.push_back(q);
+          }
+          h->h_group_off.push_back((int32_t)gorder.size());
+        }
+      }
+      if (!gorder.empty() || h->h_order.empty() || h->coloured_with_groups)
+        colour_patches(h);
+      h->coloured_with_groups = !gorder.empty();
+      std::copy(gorder.begin(), gorder.end(), h->h_order.begin());
+    }
+    else
+    {
+      // the colouring of eqlb_create is still valid unless a previous BC set grouped patches
+      h->h_grouped.assign(h->nnode, 0);
+      h->h_group_off.clear();
+      if (h->coloured_with_groups || h->h_order.empty())
+        colour_patches(h);
+      h->coloured_with_groups = false;
+    }
+
+    tm.lap("set_bcs: grouping + colouring");
+    // patch records (colour-sorted)
+    h->pstride = ((size_t)h->nactive + 31) / 32 * 32;
+    if (h->pstride == 0)
+      h->pstride = 32;
+    h->d_pnode.alloc(h->pstride);
+    h->d_pncells.alloc(h->pstride);
+    h->d_pcell.alloc(h->pstride * h->ncmax);
+    h->d_pinfo.alloc(h->pstride * h->ncmax);
+    h->d_prhs.alloc(h->pstride * h->nrhs);
+    h->d_pcell.zero(h->stream);
+    h->d_pinfo.zero(h->stream);
+    {
+      // lane records: S lanes per patch for the eligible head of every segment, each
+      // segment padded to a whole number of warps (zero records: ncells = 0)
+      h->h_seg_recoff.assign(h->nseg, -1);
+      h->h_seg_lanes.assign(h->nseg, 0);
+      std::vector<int64_t> seginfo(4 * (size_t)std::max(h->nseg, 1), 0);
+      int64_t nrec = 0;
+      for (int sg = 0; sg < h->nseg; ++sg)
+      {
+        const int maxnf = h->h_colour_maxnf[sg], nfast = h->h_colour_fast[sg];
+        const int lanes = (nfast == 0 || maxnf > 16) ? 0 : (maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16));
+        seginfo[4 * sg] = h->h_colour_off[sg];
+        seginfo[4 * sg + 1] = nfast;
+        seginfo[4 * sg + 2] = lanes;
+        seginfo[4 * sg + 3] = nrec;
+        if (lanes)
+        {
+          h->h_seg_recoff[sg] = nrec;
+          h->h_seg_lanes[sg] = lanes;
+          nrec += ((int64_t)nfast * lanes + 127) / 128 * 128;
+        }
+      }
+      h->d_prec.alloc((size_t)std::max<int64_t>(nrec, 128));
+      h->d_prec.zero(h->stream);
+      h->d_seginfo.upload(seginfo.data(), seginfo.size());
+    }
+    tm.lap("set_bcs: record buffers");
+    launch_patch_builder(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    tm.lap("set_bcs: patch builder");
+    h->bcs_set = true;
+}
+
 extern "C"
 {
 
@@ -464,7 +583,6 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
       {
         if (!h || !facet_type)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs: null argument");
-        (void)local_fct_id;  // implied by the patch maps (local id of the boundary facet in its only cell)
         StageTimer tm;
         const size_t nf = h->nfct;
         // every boundary facet has to be classified for every RHS (se/Patch.cpp:464-470)
@@ -477,117 +595,107 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
           if (bflux && bflux[r])
             CUDA_CHECK(cudaMemcpy(h->d_bflux.p + (size_t)r * nb, bflux[r], nb * sizeof(double), cudaMemcpyHostToDevice));
         tm.lap("set_bcs: facet types + bflux");
-        if (node_on_stress_bnd)
+        // local_fct_id (`base::BoundaryData::_local_fct_id`): the hot path derives the cell-local id of a boundary
+        // facet from the patch maps; a caller-supplied array is validated against the mesh
+        h->d_local_fct_id.alloc(nf);
+        if (local_fct_id)
         {
-          h->d_node_on_bnd.upload(node_on_stress_bnd, h->nnode);
-          // grouped boundary patches (se/reconstruction.hpp:170-234, k == 2 only): 2-cell
-          // patches on a pure traction boundary are solved together with the adjacent
-          // patch, which then imposes weak symmetry on the accumulated global stress
-          h->h_grouped.assign(h->nnode, 0);
-          h->h_group_off.clear();
-          std::vector<int32_t> gorder;
-          if ((h->flags & EQLB_FLAG_STRESS) && h->k == 2)
-          {
-            auto ncells_of = [&](int z) { return h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]; };
-            std::vector<uint8_t> perform(h->nnode, 1);
-            for (int z = 0; z < h->nnode; ++z)
-            {
-              if (!(node_on_stress_bnd[z] && perform[z] && h->h_owned[z]) || ncells_of(z) != 2)
-                continue;
-              // adjacent_internal_patch (se/Patch.cpp:761-784)
-              int inner = -1;
-              for (int i = h->h_node_fct_off[z]; i < h->h_node_fct_off[z + 1]; ++i)
-              {
-                const int32_t fct = h->h_node_fct[i];
-                if (facet_type[fct] == EQLB_FCT_INTERNAL)
-                {
-                  inner = (h->h_fct_node[2 * fct] == z) ? h->h_fct_node[2 * fct + 1] : h->h_fct_node[2 * fct];
-                  break;
-                }
-              }
-              // group_boundary_patches (se/Patch.cpp:60-104)
-              std::vector<int32_t> grouped{inner};
-              for (int i = h->h_node_cell_off[inner]; i < h->h_node_cell_off[inner + 1]; ++i)
-                for (int j = 0; j < 3; ++j)
-                {
-                  const int32_t pnt = h->h_cell_node[3 * (size_t)h->h_node_cell[i] + j];
-                  if (node_on_stress_bnd[pnt] && std::find(grouped.begin(), grouped.end(), pnt) == grouped.end()
-                      && ncells_of(pnt) == 2)
-                    grouped.push_back(pnt);
-                }
-              if (grouped.size() < 2)
-                continue;
-              if (h->h_group_off.empty())
-                h->h_group_off.push_back(0);
-              for (int32_t q : grouped)
-              {
-                if (!perform[q] || !h->h_owned[q])
-                  throw EqlbError(EQLB_ERR_INPUT,
-                                  "Incompatible mesh! To many patches with 2 cells on neumann boundary.");
-                perform[q] = 0;
-                h->h_grouped[q] = 1;
-                gorder.push_back(q);
-              }
-              h->h_group_off.push_back((int32_t)gorder.size());
-            }
-          }
-          if (!gorder.empty() || h->h_order.empty() || h->coloured_with_groups)
-            colour_patches(h);
-          h->coloured_with_groups = !gorder.empty();
-          std::copy(gorder.begin(), gorder.end(), h->h_order.begin());
+          CUDA_CHECK(cudaMemcpy(h->d_local_fct_id.p, local_fct_id, nf, cudaMemcpyHostToDevice));
+          if (count_bad_local_fct_ids(h, h->d_local_fct_id.p) > 0)
+            throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs: local_fct_id does not match the cell-local id of a flux-BC facet");
         }
-        else
-        {
-          // the colouring of eqlb_create is still valid unless a previous BC set grouped patches
-          h->h_grouped.assign(h->nnode, 0);
-          h->h_group_off.clear();
-          if (h->coloured_with_groups || h->h_order.empty())
-            colour_patches(h);
-          h->coloured_with_groups = false;
-        }
+        finish_bcs(h, facet_type, node_on_stress_bnd, true, tm);
+      });
+}
 
-        tm.lap("set_bcs: grouping + colouring");
-        // patch records (colour-sorted)
-        h->pstride = ((size_t)h->nactive + 31) / 32 * 32;
-        if (h->pstride == 0)
-          h->pstride = 32;
-        h->d_pnode.alloc(h->pstride);
-        h->d_pncells.alloc(h->pstride);
-        h->d_pcell.alloc(h->pstride * h->ncmax);
-        h->d_pinfo.alloc(h->pstride * h->ncmax);
-        h->d_prhs.alloc(h->pstride * h->nrhs);
-        h->d_pcell.zero(h->stream);
-        h->d_pinfo.zero(h->stream);
+int eqlb_set_bcs_poly(eqlb_handle* h, const int32_t* nprime, const int32_t* const* prime_facets, const int32_t* nbc,
+                      const eqlb_fluxbc* const* bcs)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !nprime || !prime_facets || !nbc)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs_poly: null argument");
+        StageTimer tm;
+        const size_t nf = h->nfct, nb = (size_t)h->ncell * h->nrt;
+        const bool stress = (h->flags & EQLB_FLAG_STRESS) != 0;
+        h->d_facet_type.alloc((size_t)h->nrhs * nf);
+        h->d_facet_type.zero(h->stream);
+        h->d_bflux.alloc((size_t)h->nrhs * nb);
+        h->d_bflux.zero(h->stream);
+        h->d_local_fct_id.alloc(nf);
+        h->d_local_fct_id.zero(h->stream);
+        DevBuf<int32_t> d_cnt;
+        if (stress)
         {
-          // lane records: S lanes per patch for the eligible head of every segment, each
-          // segment padded to a whole number of warps (zero records: ncells = 0)
-          h->h_seg_recoff.assign(h->nseg, -1);
-          h->h_seg_lanes.assign(h->nseg, 0);
-          std::vector<int64_t> seginfo(4 * (size_t)std::max(h->nseg, 1), 0);
-          int64_t nrec = 0;
-          for (int sg = 0; sg < h->nseg; ++sg)
-          {
-            const int maxnf = h->h_colour_maxnf[sg], nfast = h->h_colour_fast[sg];
-            const int lanes = (nfast == 0 || maxnf > 16) ? 0 : (maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16));
-            seginfo[4 * sg] = h->h_colour_off[sg];
-            seginfo[4 * sg + 1] = nfast;
-            seginfo[4 * sg + 2] = lanes;
-            seginfo[4 * sg + 3] = nrec;
-            if (lanes)
-            {
-              h->h_seg_recoff[sg] = nrec;
-              h->h_seg_lanes[sg] = lanes;
-              nrec += ((int64_t)nfast * lanes + 127) / 128 * 128;
-            }
-          }
-          h->d_prec.alloc((size_t)std::max<int64_t>(nrec, 128));
-          h->d_prec.zero(h->stream);
-          h->d_seginfo.upload(seginfo.data(), seginfo.size());
+          d_cnt.alloc(h->nnode);
+          d_cnt.zero(h->stream);
+          h->d_node_on_bnd.alloc(h->nnode);
         }
-        tm.lap("set_bcs: record buffers");
-        launch_patch_builder(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        tm.lap("set_bcs: patch builder");
-        h->bcs_set = true;
+        std::vector<std::unique_ptr<DevBuf<int32_t>>> keep_i;
+        std::vector<std::unique_ptr<DevBuf<double>>> keep_d;
+        for (int r = 0; r < h->nrhs; ++r)
+        {
+          auto dp = std::make_unique<DevBuf<int32_t>>();
+          if (nprime[r] > 0)
+          {
+            if (!prime_facets[r])
+              throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs_poly: null facet list");
+            dp->upload(prime_facets[r], nprime[r]);
+          }
+          launch_bc_poly(h, r, nprime[r], dp->p, 0, nullptr, 0, nullptr, nullptr, nullptr);
+          keep_i.push_back(std::move(dp));
+          for (int b = 0; b < nbc[r]; ++b)
+          {
+            const eqlb_fluxbc& bc = bcs[r][b];
+            if (bc.nfct <= 0)
+              continue;
+            if (!bc.facets || !bc.coeffs || bc.ncoef < 1)
+              throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs_poly: FluxBC without facets or coefficients");
+            auto df = std::make_unique<DevBuf<int32_t>>();
+            auto dc = std::make_unique<DevBuf<double>>();
+            df->upload(bc.facets, bc.nfct);
+            dc->upload(bc.coeffs, (size_t)bc.nfct * bc.ncoef);
+            // (`base/BoundaryData.cpp:611-619`) nodes of traction facets of the first gdim rows are counted
+            launch_bc_poly(h, r, 0, nullptr, bc.nfct, df->p, bc.ncoef, dc->p, h->d_local_fct_id.p, (stress && r < 2) ? d_cnt.p : nullptr);
+            keep_i.push_back(std::move(df));
+            keep_d.push_back(std::move(dc));
+          }
+        }
+        std::vector<int8_t> ft((size_t)h->nrhs * nf), nob;
+        if (stress)
+        {
+          launch_bc_node_markers(h, d_cnt.p);
+          nob.resize(h->nnode);
+          CUDA_CHECK(cudaMemcpyAsync(nob.data(), h->d_node_on_bnd.p, h->nnode, cudaMemcpyDeviceToHost, h->stream));
+        }
+        // the grouping of 2-cell traction patches and the patch classification bookkeeping are host side
+        CUDA_CHECK(cudaMemcpyAsync(ft.data(), h->d_facet_type.p, ft.size(), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        tm.lap("set_bcs_poly: boundary data on device");
+        finish_bcs(h, ft.data(), stress ? nob.data() : nullptr, false, tm);
+      });
+}
+
+int eqlb_get_boundary_data(eqlb_handle* h, int8_t* facet_type, double* const* bflux, int8_t* local_fct_id, int8_t* node_on_stress_bnd)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_get_boundary_data: boundary conditions not set");
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        const size_t nf = h->nfct, nb = (size_t)h->ncell * h->nrt;
+        if (facet_type)
+          CUDA_CHECK(cudaMemcpy(facet_type, h->d_facet_type.p, (size_t)h->nrhs * nf, cudaMemcpyDeviceToHost));
+        if (bflux)
+          for (int r = 0; r < h->nrhs; ++r)
+            if (bflux[r])
+              CUDA_CHECK(cudaMemcpy(bflux[r], h->d_bflux.p + (size_t)r * nb, nb * sizeof(double), cudaMemcpyDeviceToHost));
+        if (local_fct_id && h->d_local_fct_id.p)
+          CUDA_CHECK(cudaMemcpy(local_fct_id, h->d_local_fct_id.p, nf, cudaMemcpyDeviceToHost));
+        if (node_on_stress_bnd && h->d_node_on_bnd.p)
+          CUDA_CHECK(cudaMemcpy(node_on_stress_bnd, h->d_node_on_bnd.p, h->nnode, cudaMemcpyDeviceToHost));
       });
 }
 

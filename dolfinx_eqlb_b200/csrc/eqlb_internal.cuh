@@ -205,6 +205,7 @@ struct eqlb_handle
   DevBuf<double> d_bflux;       // [nrhs][ncell*nrt] (zeros where absent)
   std::vector<uint8_t> h_has_bflux;
   DevBuf<int8_t> d_node_on_bnd;
+  DevBuf<int8_t> d_local_fct_id;  // [nfct] cell-local id of the flux-BC facets
 
   // patches
   std::vector<int32_t> h_order;       // colour-sorted node order
@@ -261,6 +262,10 @@ void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF,
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma);
 void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* const* dout);
 void launch_korn(eqlb_handle* h, double* dKorn);
+void launch_bc_poly(eqlb_handle* h, int r, int nprime, const int32_t* d_prime, int nb, const int32_t* d_fcts, int ncoef,
+                    const double* d_coeffs, int8_t* d_local_fct_id, int32_t* d_node_cnt);
+void launch_bc_node_markers(eqlb_handle* h, const int32_t* d_cnt);
+int count_bad_local_fct_ids(eqlb_handle* h, const int8_t* d_lid);
 void launch_flux_norm(eqlb_handle* h, int nfun, const double* const* dsig, double* const* dout);
 void build_k1_tables(eqlb_handle* h, const eqlb_tables* t);
 void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff,

@@ -120,12 +120,39 @@ int eqlb_set_stream(eqlb_handle* h, void* cuda_stream);
  *   facet_type  [nrhs*nfct] int8  (eqlb_facet_type)
  *   bflux[i]    [ncell*nrt] f64   boundary function of rhs i (DRT layout), may be
  *                                 NULL when rhs i has no flux BC
- *   local_fct_id[nfct]      int8  cell-local id of each flux-BC facet
+ *   local_fct_id[nfct]      int8  cell-local id of each flux-BC facet (validated against the mesh;
+ *                                 may be NULL: the hot path derives it from the patch maps)
  *   node_on_stress_bnd [nnode] int8 (stress only, else NULL)
  * Runs the device patch builder (integer maps, patch types, colouring).
  * HOST pointers. */
 int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* bflux,
                  const int8_t* local_fct_id, const int8_t* node_on_stress_bnd);
+
+/* Device-side construction of the same boundary data for tractions given as polynomials on the
+ * boundary facets: replaces the host loop of the `base::BoundaryData` constructor
+ * (`base/BoundaryData.cpp:279-633`, interpolation branch `:580-597`, `KernelDataBC::interpolate_flux
+ * :149-161,229-250`) and the FluxBC objects of `wrappers.cpp:144-232` for this case.
+ *   eqlb_fluxbc: on facet facets[i] the prescribed OUTWARD normal flux is
+ *                g(s) = sum_j coeffs[i*ncoef + j] s^j, s = facet parameter of the adjacent cell
+ *                ((1-s,s), (0,s), (s,0) for local facets 0, 1, 2)
+ *   prime_facets[r][nprime[r]]  facets with essential BCs of the primal problem of rhs r
+ *   bcs[r][nbc[r]]              flux BCs of rhs r
+ * One thread per boundary facet computes facet types, cell-local facet ids, the boundary DOFs
+ * (hierarchic facet moments, DRT layout) and - for stress problems - the node markers; then the
+ * patch builder runs as in eqlb_set_bcs.  HOST pointers. */
+typedef struct eqlb_fluxbc {
+  int32_t nfct;
+  const int32_t* facets;
+  int32_t ncoef;
+  const double* coeffs;
+} eqlb_fluxbc;
+int eqlb_set_bcs_poly(eqlb_handle* h, const int32_t* nprime, const int32_t* const* prime_facets,
+                      const int32_t* nbc, const eqlb_fluxbc* const* bcs);
+/* The boundary data resident on the device (after eqlb_set_bcs or eqlb_set_bcs_poly), for parity
+ * tests: facet_type [nrhs*nfct], bflux[r] [ncell*nrt], local_fct_id [nfct], node_on_stress_bnd
+ * [nnode] (stress handles).  Any pointer may be NULL.  HOST buffers. */
+int eqlb_get_boundary_data(eqlb_handle* h, int8_t* facet_type, double* const* bflux, int8_t* local_fct_id,
+                           int8_t* node_on_stress_bnd);
 
 /* Semi-explicit equilibration: sigma[i] += equilibrated corrector of rhs i.
  *   G[i]     [ncell*ndg*2] projected flux (blocked bs=2), f[i] [ncell*ndg] projected RHS

@@ -111,25 +111,36 @@ public:
   template <typename... Ix, typename = std::enable_if_t<sizeof...(Ix) == N>>
   constexpr T& operator()(Ix... idx) const
   {
-    const std::array<I, N> ix{static_cast<I>(idx)...};
-    I off = 0;
-    for (std::size_t i = 0; i < N; ++i)
-    {
 #ifdef EQLB_SHIM_CHECK
-      if (!(ix[i] < _e[i]))
-      {
-        std::fprintf(stderr, "mdspan shim: index %zu out of range [0,%zu) in dimension %zu\n", (std::size_t)ix[i], (std::size_t)_e[i], i);
-        void* bt[32];
-        backtrace_symbols_fd(bt, backtrace(bt, 32), 2);
-        std::abort();
-      }
-#endif
-      off += ix[i] * _s[i];
+    {
+      const std::array<I, N> ix{static_cast<I>(idx)...};
+      for (std::size_t i = 0; i < N; ++i)
+        if (!(ix[i] < _e[i]))
+        {
+          std::fprintf(stderr, "mdspan shim: index %zu out of range [0,%zu) in dimension %zu\n", (std::size_t)ix[i], (std::size_t)_e[i], i);
+          void* bt[32];
+          backtrace_symbols_fd(bt, backtrace(bt, 32), 2);
+          std::abort();
+        }
     }
-    return _p[off];
+#endif
+    return _p[offset(std::index_sequence_for<Ix...>{}, idx...)];
   }
 
 private:
+  template <std::size_t... Is, typename... Ix>
+  constexpr I offset(std::index_sequence<Is...>, Ix... idx) const
+  {
+    if constexpr (std::is_same_v<Layout, layout_right>)
+    {
+      // Horner form over the extents: no stride loads, the last index is contiguous
+      I off = 0;
+      ((off = off * _e[Is] + static_cast<I>(idx)), ...);
+      return off;
+    }
+    else
+      return ((static_cast<I>(idx) * _s[Is]) + ... + I(0));
+  }
   constexpr void set_right_strides()
   {
     I s = 1;

@@ -120,6 +120,10 @@ def ptr_array(arrays, ctype=C.c_double):
     return arr
 
 
+class EqlbFluxBC(C.Structure):
+    _fields_ = [("nfct", C.c_int32), ("facets", c_int32_p), ("ncoef", C.c_int32), ("coeffs", c_double_p)]
+
+
 _lib = None
 
 
@@ -178,6 +182,10 @@ def load_library():
     lib.eqlb_halo_destroy.restype = None
     lib.eqlb_launch_count.argtypes = [H]
     lib.eqlb_launch_count.restype = C.c_int64
+    lib.eqlb_set_bcs_poly.argtypes = [H, c_int32_p, C.POINTER(c_int32_p), c_int32_p, C.POINTER(C.POINTER(EqlbFluxBC))]
+    lib.eqlb_set_bcs_poly.restype = C.c_int
+    lib.eqlb_get_boundary_data.argtypes = [H, c_int8_p, C.POINTER(c_double_p), c_int8_p, c_int8_p]
+    lib.eqlb_get_boundary_data.restype = C.c_int
     lib.eqlb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, c_double_p]
     lib.eqlb_measure_fp64_peak.restype = C.c_int
     lib.eqlb_last_error.restype = C.c_char_p

@@ -147,6 +147,49 @@ class _Problem:
         )
         self.set_bcs_seconds = time.perf_counter() - t0  # colouring, device patch builder (C ABI call only)
 
+    def set_bcs_device(self, list_bcs, list_bfcts_prime):
+        """Boundary data built ON THE DEVICE from polynomial tractions (`eqlb_set_bcs_poly`):
+        facet types, cell-local facet ids, boundary DOFs and node markers by one thread per boundary facet -
+        replaces the host loop of `BoundaryData` above / `base/BoundaryData.cpp:279-633`."""
+        nrhs = self.nrhs
+        if len(list_bcs) != nrhs or len(list_bfcts_prime) != nrhs:
+            raise RuntimeError("Mismatching inputs!")
+        prime = [np.ascontiguousarray(p, dtype=np.int32) for p in list_bfcts_prime]
+        nprime = (C.c_int32 * nrhs)(*[p.shape[0] for p in prime])
+        nbc = (C.c_int32 * nrhs)(*[len(b) for b in list_bcs])
+        keep, rows = [], (C.POINTER(cabi.EqlbFluxBC) * nrhs)()
+        for r, bcs in enumerate(list_bcs):
+            arr = (cabi.EqlbFluxBC * max(len(bcs), 1))()
+            for i, bc in enumerate(bcs):
+                f = np.ascontiguousarray(bc.facets, dtype=np.int32)
+                co = np.ascontiguousarray(bc.coeffs, dtype=np.float64)
+                keep += [f, co]
+                arr[i] = cabi.EqlbFluxBC(f.shape[0], f.ctypes.data_as(cabi.c_int32_p), co.shape[1], co.ctypes.data_as(cabi.c_double_p))
+            keep.append(arr)
+            rows[r] = C.cast(arr, C.POINTER(cabi.EqlbFluxBC))
+        t0 = time.perf_counter()
+        _check(self.lib, self.lib.eqlb_set_bcs_poly(self.h, nprime, cabi.ptr_array(prime, C.c_int32), nbc, rows))
+        self.set_bcs_seconds = time.perf_counter() - t0
+
+    def boundary_data(self):
+        """Boundary data resident on the device (`eqlb_get_boundary_data`), as a `BoundaryData`-like object."""
+        m, T = self.mesh, self.tables
+
+        class _BD:
+            pass
+
+        bd = _BD()
+        bd.facet_type = np.zeros((self.nrhs, m.nfct), np.int8)
+        bd.bflux = [np.zeros(m.ncell * T.nrt) for _ in range(self.nrhs)]
+        bd.local_fct_id = np.zeros(m.nfct, np.int8)
+        bd.node_on_stress_bnd = np.zeros(m.nnode, np.int8) if self.stress else None
+        nob = bd.node_on_stress_bnd
+        _check(self.lib, self.lib.eqlb_get_boundary_data(
+            self.h, bd.facet_type.ctypes.data_as(cabi.c_int8_p), cabi.ptr_array(bd.bflux),
+            bd.local_fct_id.ctypes.data_as(cabi.c_int8_p), nob.ctypes.data_as(cabi.c_int8_p) if nob is not None else cabi.c_int8_p()))
+        bd.num_rhs = self.nrhs
+        return bd
+
     def launch_count(self):
         return int(self.lib.eqlb_launch_count(self.h))
 
@@ -307,9 +350,16 @@ class FluxEqlbSE(FluxEquilibrator):
         if host_pipeline:
             self._pin(self.list_flux + list(list_rhs) + list(list_proj_flux))
 
-    def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
+    def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux, device=False):
+        """`device=True`: the boundary data are built on the GPU (`eqlb_set_bcs_poly`); else by the host mirror
+        `BoundaryData` and uploaded (`eqlb_set_bcs`).  Same result (tests/test_gpu_bcs.py)."""
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
             raise RuntimeError("Mismatching inputs!")
+        if device:
+            self.problem.set_bcs_device(list_bcs_flux, list_bfct_prime)
+            self.boundary_data = self.problem.boundary_data()
+            self.list_bfunctions = self.boundary_data.bflux
+            return
         self.boundary_data = boundarydata(list_bcs_flux, self.mesh, self.tables, list_bfct_prime, self.equilibrate_stresses)
         self.list_bfunctions = self.boundary_data.bflux
         self.problem.set_bcs(self.boundary_data)
@@ -355,9 +405,14 @@ class FluxEqlbEV(FluxEquilibrator):
         if host_pipeline:
             self._pin(self.list_flux + list(list_rhs) + list(list_proj_flux))
 
-    def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux):
+    def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux, device=False):
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
             raise RuntimeError("Mismatching inputs!")
+        if device:
+            self.problem.set_bcs_device(list_bcs_flux, list_bfct_prime)
+            self.boundary_data = self.problem.boundary_data()
+            self.list_bfunctions = self.boundary_data.bflux
+            return
         self.boundary_data = boundarydata(list_bcs_flux, self.mesh, self.tables, list_bfct_prime, False)
         self.list_bfunctions = self.boundary_data.bflux
         self.problem.set_bcs(self.boundary_data)

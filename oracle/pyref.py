@@ -80,6 +80,11 @@ def lib():
             C.POINTER(EqlbMesh), C.POINTER(RefElement), C.c_int, c_int8_p, C.POINTER(c_double_p),
             C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p),
         ]
+        L.ref_boundary_data.restype = C.c_int
+        L.ref_boundary_data.argtypes = [
+            C.POINTER(EqlbMesh), C.POINTER(RefElement), C.c_int, C.c_int, C.c_int, c_int32_p, C.POINTER(c_int32_p), c_int32_p,
+            C.POINTER(c_int32_p), C.c_int, C.POINTER(c_double_p), c_int8_p, C.POINTER(c_double_p), c_int8_p,
+        ]
         _lib = L
     return _lib
 
@@ -207,3 +212,38 @@ def ev_run(mesh, tables, bc, G, F, sigma0=None):
     )
     _check(rc)
     return sig
+
+
+def boundary_data(mesh, tables, list_bcs, list_bfct_prime, stress=False, qdegree_proj=-1):
+    """The reference's `base::BoundaryData` constructor with polynomial FluxBC kernels
+    (`list_bcs[r]` = list of objects with `.facets`, `.coeffs`).  qdegree_proj < 0: interpolation branch,
+    else the facet-local projection branch with that quadrature degree.
+    Returns (facet_type [nrhs][nfct], bflux list, node_on_stress_bnd or None)."""
+    pm, pe = PackedMesh(mesh, tables.ndg), PackedElement(tables.k, tables.p)
+    nrhs = len(list_bcs)
+    fc, cf = [], []
+    ncoef = 1
+    for bcs in list_bcs:
+        for bc in bcs:
+            ncoef = max(ncoef, bc.coeffs.shape[1])
+    for bcs in list_bcs:
+        f = np.concatenate([bc.facets for bc in bcs]).astype(np.int32) if bcs else np.zeros(0, np.int32)
+        c = np.zeros((f.shape[0], ncoef))
+        o = 0
+        for bc in bcs:
+            c[o : o + bc.facets.shape[0], : bc.coeffs.shape[1]] = bc.coeffs
+            o += bc.facets.shape[0]
+        fc.append(np.ascontiguousarray(f))
+        cf.append(np.ascontiguousarray(c))
+    pr_ = [np.ascontiguousarray(p, dtype=np.int32) for p in list_bfct_prime]
+    i32 = lambda xs: (C.c_int32 * len(xs))(*xs)
+    ft = np.zeros((nrhs, mesh.nfct), np.int8)
+    bv = [np.zeros(mesh.ncell * tables.nrt) for _ in range(nrhs)]
+    nob = np.zeros(mesh.nnode, np.int8)
+    rc = lib().ref_boundary_data(
+        C.byref(pm.struct), C.byref(pe.struct), nrhs, int(stress), int(qdegree_proj), i32([p.shape[0] for p in pr_]),
+        ptr_array(pr_, C.c_int32), i32([f.shape[0] for f in fc]), ptr_array(fc, C.c_int32), ncoef, ptr_array(cf),
+        _i8(ft), ptr_array(bv), _i8(nob),
+    )
+    _check(rc)
+    return ft, bv, (nob if stress else None)

@@ -839,3 +839,126 @@ int ref_ev_run(const eqlb_mesh* mesh, const ref_element* elmt, int nrhs, const i
       });
 }
 }
+
+extern "C"
+{
+/// The reference's `base::BoundaryData` CONSTRUCTOR (`base/BoundaryData.cpp:279-633`) with FluxBC objects
+/// (`base/FluxBC.hpp`) whose boundary kernel evaluates a polynomial normal traction: on facet fcts[i] of
+/// rhs r the prescribed outward normal flux is g(s) = sum_j coeffs[i*ncoef+j] s^j, s = facet parameter of the
+/// adjacent cell.  Interpolation branch (`:580-597`) when qdegree_proj < 0, projection branch (`:511-578`)
+/// otherwise (the kernel is then evaluated at the facet quadrature points).
+///   nbc[r] facets per rhs, fcts[r], coeffs[r]; prime[r] (nprime[r]) Dirichlet facets of the primal problem.
+/// Outputs (any may be null): facet_type [nrhs][nfct], bvals[r] [ncell*nrt] (DRT boundary function),
+/// node_on_bnd [nnode] (stress).
+int ref_boundary_data(const eqlb_mesh* mesh, const ref_element* elmt, int nrhs, int stress, int qdegree_proj, const int32_t* nprime,
+                      const int32_t* const* prime, const int32_t* nbc, const int32_t* const* fcts, int ncoef,
+                      const double* const* coeffs, int8_t* facet_type, double* const* bvals, int8_t* node_on_bnd)
+{
+  return guarded(
+      [&]
+      {
+        Spaces sp(mesh, elmt);
+        const int k = elmt->k;
+        const size_t n = (size_t)mesh->ncell * sp.nrt;
+        // coefficient function of the traction: per cell [local facet][ncoef] (DG-like space, identity dofmap)
+        const int nloc = 3 * ncoef;
+        std::vector<std::int32_t> ident((size_t)mesh->ncell * nloc);
+        for (size_t i = 0; i < ident.size(); ++i)
+          ident[i] = (std::int32_t)i;
+        basix::FiniteElement dg0 = basix::element::create_lagrange(basix::cell::type::triangle, 0,
+                                                                    basix::element::lagrange_variant::equispaced, true);
+        auto el_tr = std::make_shared<fem::FiniteElement>(dg0, 1);
+        el_tr->set_space_dimension(nloc);
+        auto V_tr = std::make_shared<fem::FunctionSpace>(
+            sp.mesh, el_tr,
+            std::make_shared<const fem::DofMap>(AL::regular(ident.data(), mesh->ncell, nloc), mesh->ncell * nloc, 1,
+                                                fem::ElementDofLayout(dg0.entity_dofs())));
+        // evaluation points per facet: interpolation points of the flux element or the facet quadrature points
+        const bool project = qdegree_proj >= 0;
+        const int qdeg = project ? qdegree_proj : 2 * (k - 1);
+        std::vector<double> s_pts;  // facet parameter of the evaluation points
+        if (project)
+        {
+          auto q = basix::quadrature::make_quadrature(basix::cell::type::interval, qdeg);
+          s_pts = q[0];
+        }
+        else
+        {
+          // facet 1 interpolation points are (0, s): read s from the element's point list
+          int nip = 0;
+          while (elmt->X[2 * nip] > 0.0)
+            ++nip;
+          for (int i = 0; i < nip; ++i)
+            s_pts.push_back(elmt->X[2 * (nip + i) + 1]);
+        }
+        const int nev = (int)s_pts.size();
+        std::function<void(double*, const double*, const double*, const double*, const int*, const std::uint8_t*)> kern
+            = [s_pts, nev, ncoef](double* v, const double* w, const double*, const double*, const int*, const std::uint8_t*)
+        {
+          for (int f = 0; f < 3; ++f)
+            for (int l = 0; l < nev; ++l)
+            {
+              double g = 0.0, sp_ = 1.0;
+              for (int j = 0; j < ncoef; ++j)
+              {
+                g += w[f * ncoef + j] * sp_;
+                sp_ *= s_pts[l];
+              }
+              v[f * nev + l] = g;
+            }
+        };
+        std::vector<std::vector<double>> tr(nrhs), bv(nrhs);
+        std::vector<std::vector<std::shared_ptr<eqlb::base::FluxBC<double>>>> bcs(nrhs);
+        std::vector<std::shared_ptr<fem::Function<double>>> bfuncs;
+        std::vector<std::vector<std::int32_t>> fct_prime(nrhs);
+        for (int r = 0; r < nrhs; ++r)
+        {
+          tr[r].assign((size_t)mesh->ncell * nloc, 0.0);
+          for (int i = 0; i < nbc[r]; ++i)
+          {
+            const std::int32_t f = fcts[r][i];
+            const std::int32_t c = mesh->fct_cell[mesh->fct_cell_off[f]];
+            int fl = 0;
+            for (int j = 0; j < 3; ++j)
+              if (mesh->cell_fct[3 * c + j] == f)
+                fl = j;
+            for (int j = 0; j < ncoef; ++j)
+              tr[r][(size_t)c * nloc + fl * ncoef + j] = coeffs[r][(size_t)i * ncoef + j];
+          }
+          auto trf = std::make_shared<const fem::Function<double>>(V_tr, std::make_shared<la::Vector<double>>(tr[r].data(), tr[r].size()));
+          if (nbc[r] > 0)
+          {
+            std::vector<std::int32_t> fl(fcts[r], fcts[r] + nbc[r]);
+            std::vector<std::shared_ptr<const fem::Function<double>>> cf{trf};
+            if (project)
+              bcs[r].push_back(std::make_shared<eqlb::base::FluxBC<double>>(sp.V_hdiv, fl, kern, nev, qdeg, cf, std::vector<int>{0},
+                                                                             std::vector<std::shared_ptr<const fem::Constant<double>>>{}));
+            else
+              bcs[r].push_back(std::make_shared<eqlb::base::FluxBC<double>>(sp.V_hdiv, fl, kern, nev, cf, std::vector<int>{0},
+                                                                             std::vector<std::shared_ptr<const fem::Constant<double>>>{}));
+          }
+          bv[r].assign(n, 0.0);
+          bfuncs.push_back(std::make_shared<fem::Function<double>>(sp.V_hdiv, std::make_shared<la::Vector<double>>(bv[r].data(), n)));
+          fct_prime[r].assign(prime[r], prime[r] + nprime[r]);
+        }
+        eqlb::base::BoundaryData<double> bd(bcs, bfuncs, sp.V_hdiv, true, qdeg, fct_prime, stress != 0);
+        if (facet_type)
+        {
+          auto ft = bd.facet_type();
+          for (int r = 0; r < nrhs; ++r)
+            for (int f = 0; f < mesh->nfct; ++f)
+              facet_type[(size_t)r * mesh->nfct + f] = ft(r, f);
+        }
+        if (bvals)
+          for (int r = 0; r < nrhs; ++r)
+            if (bvals[r])
+              std::memcpy(bvals[r], bv[r].data(), n * sizeof(double));
+        if (node_on_bnd && stress)
+        {
+          auto nb = bd.node_on_essnt_boundary_stress();
+          for (int i = 0; i < mesh->nnode; ++i)
+            node_on_bnd[i] = nb[i];
+        }
+      });
+}
+}

@@ -47,12 +47,13 @@ class EqlbMesh(C.Structure):
 
 _TABLE_DOUBLES = ["qpts", "qwts", "fpts_s", "fwts", "M", "rt_q", "rt_f", "dg_q", "dg_f", "hat_q", "hat_f", "trafo"]
 _TABLE_INTS = ["fct_closure", "div_lm"]
-_TABLE_REF = ["rt_mass", "fct_mom", "cell_mom_f", "cell_mom_g", "bc_mat", "rt_p1", "dg_mono", "hat_dg_rt", "mono_int"]
+_TABLE_REF = ["rt_mass", "fct_mom", "cell_mom_f", "cell_mom_g", "bc_mat", "rt_p1", "dg_mono", "hat_dg_rt", "mono_int",
+              "rt_basix_fct", "rt_basix_int", "pk_grad_dg", "pk_to_dg", "pk_q", "pk_gq", "pk_hq", "rt_div_q"]
 
 
 class EqlbTables(C.Structure):
     _fields_ = (
-        [(n, C.c_int32) for n in ["k", "p", "nrt", "ndg", "ndg_fct", "nq", "nqf", "ndiv", "nadd"]]
+        [(n, C.c_int32) for n in ["k", "p", "nrt", "ndg", "ndg_fct", "nq", "nqf", "ndiv", "nadd", "npk"]]
         + [(n, c_double_p) for n in _TABLE_DOUBLES]
         + [(n, c_int32_p) for n in _TABLE_INTS]
         + [(n, c_double_p) for n in _TABLE_REF]
@@ -95,10 +96,12 @@ class PackedTables:
         self.tables = tables
         self._keep = {}
         s = EqlbTables()
-        for n in ["k", "p", "nrt", "ndg", "ndg_fct", "nq", "nqf", "ndiv", "nadd"]:
+        for n in ["k", "p", "nrt", "ndg", "ndg_fct", "nq", "nqf", "ndiv", "nadd", "npk"]:
             setattr(s, n, getattr(tables, n))
         for n in _TABLE_DOUBLES + _TABLE_REF:
             a = np.ascontiguousarray(getattr(tables, n), dtype=np.float64)
+            if a.size == 0:
+                a = np.zeros(2)
             self._keep[n] = a
             setattr(s, n, _ptr(a, C.c_double))
         for n in _TABLE_INTS:
@@ -186,6 +189,21 @@ def load_library():
     lib.eqlb_set_bcs_poly.restype = C.c_int
     lib.eqlb_get_boundary_data.argtypes = [H, c_int8_p, C.POINTER(c_double_p), c_int8_p, c_int8_p]
     lib.eqlb_get_boundary_data.restype = C.c_int
+    lib.eqlb_ev_to_basix_rt.argtypes = [H, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p), C.c_int]
+    lib.eqlb_ev_to_basix_rt.restype = C.c_int
+    PP = C.POINTER(c_double_p)
+    lib.eqlb_set_primal_space.argtypes = [H, c_int32_p, C.c_int64]
+    lib.eqlb_set_primal_space.restype = C.c_int
+    lib.eqlb_project_primal.argtypes = [H, C.c_int, PP, PP, PP, PP, C.c_int]
+    lib.eqlb_project_primal.restype = C.c_int
+    lib.eqlb_ev_run_primal.argtypes = [H, PP, PP, PP, C.c_int]
+    lib.eqlb_ev_run_primal.restype = C.c_int
+    lib.eqlb_se_run_primal.argtypes = [H, PP, PP, PP, c_double_p, C.c_int]
+    lib.eqlb_se_run_primal.restype = C.c_int
+    lib.eqlb_estimate_poisson.argtypes = [H, C.c_int, PP, PP, PP, PP, PP, C.c_int, C.c_int]
+    lib.eqlb_estimate_poisson.restype = C.c_int
+    lib.eqlb_estimate_elasticity.argtypes = [H, PP, PP, PP, c_double_p, C.c_double, PP, C.c_int]
+    lib.eqlb_estimate_elasticity.restype = C.c_int
     lib.eqlb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, c_double_p]
     lib.eqlb_measure_fp64_peak.restype = C.c_int
     lib.eqlb_last_error.restype = C.c_char_p

@@ -9,6 +9,8 @@
 #include <memory>
 
 #include <chrono>
+#include <exception>
+#include <thread>
 
 #include "eqlb_internal.cuh"
 
@@ -424,6 +426,56 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
           h->nactive += o ? 1 : 0;
 
         const size_t nn = mesh->nnode, nc = mesh->ncell, nf = mesh->nfct;
+        // host work that does not touch the device runs beside the uploads: the greedy colouring (reads the
+        // caller's topology arrays) and, for stress handles, the topology copies eqlb_set_bcs needs later
+        // (boundary-patch grouping, recolouring).  Measured at 1024^2: upload 64-180 ms, colouring 55 ms, copies 72 ms.
+        h->h_grouped.assign(nn, 0);
+        h->topo = {mesh->node_cell_off, mesh->node_cell, mesh->cell_node, mesh->node_fct_off, mesh->node_fct, mesh->fct_node};
+        std::exception_ptr colour_err, copy_err;
+        eqlb_handle* hp = h.get();
+        std::thread colour_thread(
+            [hp, &colour_err]
+            {
+              try
+              {
+                colour_patches(hp);
+              }
+              catch (...)
+              {
+                colour_err = std::current_exception();
+              }
+            });
+        std::thread copy_thread(
+            [hp, mesh, nn, nc, nf, flags, &copy_err]
+            {
+              try
+              {
+                if (flags & EQLB_FLAG_STRESS)
+                {
+                  hp->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
+                  hp->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
+                  hp->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
+                  hp->h_node_fct_off.assign(mesh->node_fct_off, mesh->node_fct_off + nn + 1);
+                  hp->h_node_fct.assign(mesh->node_fct, mesh->node_fct + mesh->node_fct_off[nn]);
+                  hp->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
+                }
+              }
+              catch (...)
+              {
+                copy_err = std::current_exception();
+              }
+            });
+        struct Joiner
+        {
+          std::thread &a, &b;
+          ~Joiner()
+          {
+            if (a.joinable())
+              a.join();
+            if (b.joinable())
+              b.join();
+          }
+        } joiner{colour_thread, copy_thread};
         h->d_x.upload(mesh->x, nn * 3);
         h->d_cell_node.upload(mesh->cell_node, nc * 3);
         h->d_cell_fct.upload(mesh->cell_fct, nc * 3);
@@ -436,23 +488,6 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
         h->d_fct_perms.upload(mesh->fct_perms, nc * 3);
         tm.lap("create: mesh upload");
-        // host topology: colouring reads the caller's arrays; only stress handles keep copies
-        // (boundary-patch grouping and recolouring in eqlb_set_bcs)
-        h->topo = {mesh->node_cell_off, mesh->node_cell, mesh->cell_node, mesh->node_fct_off, mesh->node_fct, mesh->fct_node};
-        if (flags & EQLB_FLAG_STRESS)
-        {
-          h->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
-          h->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
-          h->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
-          h->h_node_fct_off.assign(mesh->node_fct_off, mesh->node_fct_off + nn + 1);
-          h->h_node_fct.assign(mesh->node_fct, mesh->node_fct + mesh->node_fct_off[nn]);
-          h->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
-          h->topo = {h->h_node_cell_off.data(), h->h_node_cell.data(), h->h_cell_node.data(),
-                     h->h_node_fct_off.data(), h->h_node_fct.data(), h->h_fct_node.data()};
-        }
-        h->h_grouped.assign(nn, 0);
-
-        tm.lap("create: host copies");
         // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
         h->dg_identity = true;
         if (mesh->dg_dofmap)
@@ -490,6 +525,35 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         append(flat, t->hat_dg_rt, (size_t)3 * ndg * nrt * 2, tv.o_hat_dg_rt);
         append(flat, t->mono_int, (size_t)nt, tv.o_mono_int);
         h->d_tables.upload(flat.data(), flat.size());
+        if (t->rt_basix_fct && t->rt_basix_int)
+        {
+          std::vector<double> bx(t->rt_basix_fct, t->rt_basix_fct + (size_t)k * k);
+          bx.insert(bx.end(), t->rt_basix_int, t->rt_basix_int + (size_t)(k * k - k) * nrt);
+          bx.push_back(0.0);
+          h->d_basix.upload(bx.data(), bx.size());
+        }
+        h->npk = t->npk;
+        if (t->pk_q && t->pk_gq && t->pk_hq && t->rt_div_q && t->pk_grad_dg && t->pk_to_dg && t->npk > 0)
+        {
+          // [qwts | rt_q | rt_div_q | pk_q | pk_gq | pk_hq | dg_q | pk_grad_dg | pk_to_dg]
+          std::vector<double> pr;
+          const int nq = t->nq, npk = t->npk;
+          auto put = [&](int slot, const double* src, size_t n)
+          {
+            h->o_pr[slot] = (int)pr.size();
+            pr.insert(pr.end(), src, src + n);
+          };
+          put(0, t->qwts, nq);
+          put(1, t->rt_q, (size_t)nq * nrt * 2);
+          put(2, t->rt_div_q, (size_t)nq * nrt);
+          put(3, t->pk_q, (size_t)nq * npk);
+          put(4, t->pk_gq, (size_t)nq * npk * 2);
+          put(5, t->pk_hq, (size_t)nq * npk * 3);
+          put(6, t->dg_q, (size_t)3 * nq * ndg);
+          put(7, t->pk_grad_dg, (size_t)ndg * npk * 2);
+          put(8, t->pk_to_dg, (size_t)ndg * npk);
+          h->d_primal.upload(pr.data(), pr.size());
+        }
         tv.data = h->d_tables.p;
         tv.ndoubles = (int)flat.size();
 
@@ -552,10 +616,19 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         tm.lap("create: tables");
         launch_compute_cellJ(h.get());
         tm.lap("create: cell Jacobians");
-        colour_patches(h.get());
-        if (!(flags & EQLB_FLAG_STRESS))
-          h->topo = {};  // the caller's arrays are not referenced after eqlb_create
-        tm.lap("create: colouring");
+        colour_thread.join();
+        copy_thread.join();
+        if (colour_err)
+          std::rethrow_exception(colour_err);
+        if (copy_err)
+          std::rethrow_exception(copy_err);
+        // the caller's arrays are not referenced after eqlb_create: stress handles switch to their copies
+        if (flags & EQLB_FLAG_STRESS)
+          h->topo = {h->h_node_cell_off.data(), h->h_node_cell.data(), h->h_cell_node.data(),
+                     h->h_node_fct_off.data(), h->h_node_fct.data(), h->h_fct_node.data()};
+        else
+          h->topo = {};
+        tm.lap("create: wait for colouring / topology copies");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         *out = h.release();
       });
@@ -588,10 +661,16 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
         // every boundary facet has to be classified for every RHS (se/Patch.cpp:464-470)
         h->d_facet_type.upload(facet_type, (size_t)h->nrhs * nf);
         const size_t nb = (size_t)h->ncell * h->nrt;
-        h->d_bflux.alloc((size_t)h->nrhs * nb);
+        // the boundary function is only read on cells with a flux-BC facet: without any such facet no
+        // [nrhs][ncell*nrt] array is allocated (268 MB + zero fill per RHS at 1024^2, degree 2)
+        bool any_dual = false;
+        for (size_t i = 0; i < (size_t)h->nrhs * nf && !any_dual; ++i)
+          any_dual = facet_type[i] == EQLB_FCT_ESSNT_DUAL;
+        h->bflux_dummy = !any_dual;
+        h->d_bflux.alloc(any_dual ? (size_t)h->nrhs * nb : 2);
         h->d_bflux.zero(h->stream);
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        for (int r = 0; r < h->nrhs; ++r)
+        for (int r = 0; r < h->nrhs && any_dual; ++r)
           if (bflux && bflux[r])
             CUDA_CHECK(cudaMemcpy(h->d_bflux.p + (size_t)r * nb, bflux[r], nb * sizeof(double), cudaMemcpyHostToDevice));
         tm.lap("set_bcs: facet types + bflux");
@@ -621,7 +700,12 @@ int eqlb_set_bcs_poly(eqlb_handle* h, const int32_t* nprime, const int32_t* cons
         const bool stress = (h->flags & EQLB_FLAG_STRESS) != 0;
         h->d_facet_type.alloc((size_t)h->nrhs * nf);
         h->d_facet_type.zero(h->stream);
-        h->d_bflux.alloc((size_t)h->nrhs * nb);
+        int64_t nbcf = 0;
+        for (int r = 0; r < h->nrhs; ++r)
+          for (int b = 0; b < nbc[r]; ++b)
+            nbcf += bcs[r][b].nfct;
+        h->bflux_dummy = nbcf == 0;
+        h->d_bflux.alloc(nbcf ? (size_t)h->nrhs * nb : 2);
         h->d_bflux.zero(h->stream);
         h->d_local_fct_id.alloc(nf);
         h->d_local_fct_id.zero(h->stream);
@@ -691,7 +775,12 @@ int eqlb_get_boundary_data(eqlb_handle* h, int8_t* facet_type, double* const* bf
         if (bflux)
           for (int r = 0; r < h->nrhs; ++r)
             if (bflux[r])
-              CUDA_CHECK(cudaMemcpy(bflux[r], h->d_bflux.p + (size_t)r * nb, nb * sizeof(double), cudaMemcpyDeviceToHost));
+            {
+              if (h->bflux_dummy)
+                std::memset(bflux[r], 0, nb * sizeof(double));
+              else
+                CUDA_CHECK(cudaMemcpy(bflux[r], h->d_bflux.p + (size_t)r * nb, nb * sizeof(double), cudaMemcpyDeviceToHost));
+            }
         if (local_fct_id && h->d_local_fct_id.p)
           CUDA_CHECK(cudaMemcpy(local_fct_id, h->d_local_fct_id.p, nf, cudaMemcpyDeviceToHost));
         if (node_on_stress_bnd && h->d_node_on_bnd.p)
@@ -1152,6 +1241,280 @@ int eqlb_flux_l2norm(eqlb_handle* h, int nfun, const double* const* sigma, doubl
       });
 }
 
+int eqlb_ev_to_basix_rt(eqlb_handle* h, int nfun, const double* const* sigma_hier, double* const* sigma_basix, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !sigma_hier || !sigma_basix || nfun < 1)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_ev_to_basix_rt: bad argument");
+        if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_ev_to_basix_rt: memspace must be EQLB_HOST or EQLB_DEVICE");
+        const size_t n = (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k);
+        std::vector<const double*> din(nfun);
+        std::vector<double*> dout(nfun);
+        DevBuf<double> st_in, st_out;
+        for (int i = 0; i < nfun; ++i)
+          if (sigma_hier[i] == sigma_basix[i])
+            throw EqlbError(EQLB_ERR_INPUT, "eqlb_ev_to_basix_rt: conversion is out of place");
+        if (memspace == EQLB_DEVICE)
+          for (int i = 0; i < nfun; ++i)
+          {
+            din[i] = sigma_hier[i];
+            dout[i] = sigma_basix[i];
+          }
+        else
+        {
+          st_in.alloc(n * nfun);
+          st_out.alloc(n * nfun);
+          for (int i = 0; i < nfun; ++i)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(st_in.p + i * n, sigma_hier[i], n * 8, cudaMemcpyHostToDevice, h->stream));
+            din[i] = st_in.p + i * n;
+            dout[i] = st_out.p + i * n;
+          }
+        }
+        launch_ev_to_basix(h, nfun, din.data(), dout.data());
+        if (memspace != EQLB_DEVICE)
+        {
+          for (int i = 0; i < nfun; ++i)
+            CUDA_CHECK(cudaMemcpyAsync(sigma_basix[i], dout[i], n * 8, cudaMemcpyDeviceToHost, h->stream));
+          CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        }
+      });
+}
+
 int64_t eqlb_launch_count(eqlb_handle* h) { return h ? h->launches : 0; }
 
+} // extern "C"
+
+namespace
+{
+// device views of caller vectors: the pointers themselves (EQLB_DEVICE) or staged copies (host)
+struct Staged
+{
+  std::vector<std::unique_ptr<DevBuf<double>>> bufs;
+  std::vector<const double*> in(eqlb_handle* h, int n, const double* const* v, size_t len, bool host)
+  {
+    std::vector<const double*> out(n, nullptr);
+    for (int i = 0; i < n; ++i)
+    {
+      if (!v || !v[i])
+        continue;
+      if (!host)
+      {
+        out[i] = v[i];
+        continue;
+      }
+      auto b = std::make_unique<DevBuf<double>>();
+      b->alloc(len);
+      CUDA_CHECK(cudaMemcpyAsync(b->p, v[i], len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      out[i] = b->p;
+      bufs.push_back(std::move(b));
+    }
+    return out;
+  }
+  std::vector<double*> out(eqlb_handle* h, int n, double* const* v, size_t len, bool host, bool upload)
+  {
+    std::vector<double*> o(n, nullptr);
+    for (int i = 0; i < n; ++i)
+    {
+      if (!v || !v[i])
+        continue;
+      if (!host)
+      {
+        o[i] = v[i];
+        continue;
+      }
+      auto b = std::make_unique<DevBuf<double>>();
+      b->alloc(len);
+      if (upload)
+        CUDA_CHECK(cudaMemcpyAsync(b->p, v[i], len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      else
+        b->zero(h->stream);
+      o[i] = b->p;
+      bufs.push_back(std::move(b));
+    }
+    return o;
+  }
+  static void back(eqlb_handle* h, int n, double* const* host, const std::vector<double*>& dev, size_t len)
+  {
+    for (int i = 0; i < n; ++i)
+      if (host && host[i] && dev[i])
+        CUDA_CHECK(cudaMemcpyAsync(host[i], dev[i], len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+};
+
+void check_memspace3(int memspace, const char* who)
+{
+  if (memspace != EQLB_HOST && memspace != EQLB_DEVICE && memspace != EQLB_HOST_ZEROED)
+    throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": memspace must be EQLB_HOST, EQLB_DEVICE or EQLB_HOST_ZEROED");
+}
+
+// projection + equilibration: G, F live in device scratch only
+void run_primal(eqlb_handle* h, bool ev, const double* const* uh, const double* const* fh, double* const* sigma, double* korn,
+                int memspace)
+{
+  if (!h || !uh || !fh || !sigma)
+    throw EqlbError(EQLB_ERR_INPUT, "eqlb_*_run_primal: null argument");
+  if (!h->bcs_set)
+    throw EqlbError(EQLB_ERR_STATE, "boundary conditions not set (eqlb_set_bcs)");
+  check_memspace3(memspace, "eqlb_*_run_primal");
+  const bool host = memspace != EQLB_DEVICE;
+  const int n = h->nrhs;
+  const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg;
+  const size_t nS = ev ? (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k) : (size_t)h->ncell * h->nrt;
+  Staged st;
+  auto du = st.in(h, n, uh, (size_t)h->pk_ndofs, host);
+  auto df = st.in(h, n, fh, (size_t)h->pk_ndofs, host);
+  h->d_stage_G.alloc(nG * n);
+  h->d_stage_f.alloc(nF * n);
+  std::vector<double*> G(n), F(n);
+  std::vector<const double*> Gc(n), Fc(n);
+  for (int i = 0; i < n; ++i)
+  {
+    G[i] = h->d_stage_G.p + i * nG;
+    F[i] = h->d_stage_f.p + i * nF;
+    Gc[i] = G[i];
+    Fc[i] = F[i];
+  }
+  launch_primal_project(h, n, du.data(), df.data(), G.data(), F.data());
+  auto dS = st.out(h, n, sigma, nS, host, memspace == EQLB_HOST);
+  DevBuf<double> dk;
+  double* dkorn = korn;
+  if (korn && host)
+  {
+    dk.alloc(h->ncell);
+    CUDA_CHECK(cudaMemcpyAsync(dk.p, korn, (size_t)h->ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    dkorn = dk.p;
+  }
+  if (ev)
+    launch_ev(h, Gc.data(), Fc.data(), dS.data());
+  else
+    launch_se(h, Gc.data(), Fc.data(), dS.data(), dkorn);
+  if (host)
+  {
+    if (korn)
+      CUDA_CHECK(cudaMemcpyAsync(korn, dkorn, (size_t)h->ncell * 8, cudaMemcpyDeviceToHost, h->stream));
+    Staged::back(h, n, sigma, dS, nS);
+  }
+}
+} // namespace
+
+extern "C"
+{
+int eqlb_set_primal_space(eqlb_handle* h, const int32_t* pk_dofmap, int64_t ndofs)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !pk_dofmap || ndofs < 1)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_primal_space: bad argument");
+        if (h->npk < 1 || !h->d_primal.p)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_set_primal_space: the tables carry no primal-space data (pk_*)");
+        const size_t n = (size_t)h->ncell * h->npk;
+        for (size_t i = 0; i < n; ++i)
+          if (pk_dofmap[i] < 0 || pk_dofmap[i] >= ndofs)
+            throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_primal_space: dofmap entry out of range");
+        h->d_pk_dofmap.upload(pk_dofmap, n);
+        h->pk_ndofs = ndofs;
+      });
+}
+
+int eqlb_project_primal(eqlb_handle* h, int nfun, const double* const* uh, const double* const* fh, double* const* G,
+                        double* const* F, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || nfun < 1)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_project_primal: bad argument");
+        if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_project_primal: memspace must be EQLB_HOST or EQLB_DEVICE");
+        const bool host = memspace == EQLB_HOST;
+        const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg;
+        Staged st;
+        auto du = st.in(h, nfun, uh, (size_t)h->pk_ndofs, host);
+        auto df = st.in(h, nfun, fh, (size_t)h->pk_ndofs, host);
+        auto dG = st.out(h, nfun, G, nG, host, false);
+        auto dF = st.out(h, nfun, F, nF, host, false);
+        for (int i = 0; i < nfun; ++i)
+          if ((du[i] && !dG[i]) || (df[i] && !dF[i]))
+            throw EqlbError(EQLB_ERR_INPUT, "eqlb_project_primal: output missing for a given input");
+        launch_primal_project(h, nfun, du.data(), df.data(), dG.data(), dF.data());
+        if (host)
+        {
+          Staged::back(h, nfun, G, dG, nG);
+          Staged::back(h, nfun, F, dF, nF);
+        }
+      });
+}
+
+int eqlb_ev_run_primal(eqlb_handle* h, const double* const* uh, const double* const* fh, double* const* sigma, int memspace)
+{
+  return guarded([&] { run_primal(h, true, uh, fh, sigma, nullptr, memspace); });
+}
+
+int eqlb_se_run_primal(eqlb_handle* h, const double* const* uh, const double* const* fh, double* const* sigma, double* korn,
+                       int memspace)
+{
+  return guarded([&] { run_primal(h, false, uh, fh, sigma, korn, memspace); });
+}
+
+int eqlb_estimate_poisson(eqlb_handle* h, int nfun, const double* const* sigma, const double* const* uh,
+                          const double* const* fh, double* const* eta_sig2, double* const* eta_osc2, int is_ev, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || nfun < 1 || !sigma || !eta_sig2 || !eta_osc2)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_poisson: bad argument");
+        if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_poisson: memspace must be EQLB_HOST or EQLB_DEVICE");
+        const bool host = memspace == EQLB_HOST;
+        const size_t nS = is_ev ? (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k) : (size_t)h->ncell * h->nrt;
+        Staged st;
+        auto dS = st.in(h, nfun, sigma, nS, host);
+        auto du = st.in(h, nfun, uh, (size_t)h->pk_ndofs, host);
+        auto df = st.in(h, nfun, fh, (size_t)h->pk_ndofs, host);
+        auto e1 = st.out(h, nfun, eta_sig2, h->ncell, host, false);
+        auto e2 = st.out(h, nfun, eta_osc2, h->ncell, host, false);
+        for (int i = 0; i < nfun; ++i)
+          if (!dS[i] || !e1[i] || !e2[i])
+            throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_poisson: null vector");
+        launch_estimate_poisson(h, nfun, dS.data(), uh ? du.data() : nullptr, fh ? df.data() : nullptr, e1.data(), e2.data(), is_ev);
+        if (host)
+        {
+          Staged::back(h, nfun, eta_sig2, e1, h->ncell);
+          Staged::back(h, nfun, eta_osc2, e2, h->ncell);
+        }
+      });
+}
+
+int eqlb_estimate_elasticity(eqlb_handle* h, const double* const* dsig, const double* const* sigma_h, const double* const* fh,
+                             const double* korn, double pi_1, double* const* eta, int memspace)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !dsig || !eta)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_elasticity: bad argument");
+        if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_elasticity: memspace must be EQLB_HOST or EQLB_DEVICE");
+        const bool host = memspace == EQLB_HOST;
+        Staged st;
+        auto dS = st.in(h, 2, dsig, (size_t)h->ncell * h->nrt, host);
+        auto dH = st.in(h, 2, sigma_h, (size_t)h->ncell * h->ndg * 2, host);
+        auto df = st.in(h, 2, fh, (size_t)h->pk_ndofs, host);
+        const double* kp[1] = {korn};
+        auto dk = st.in(h, 1, korn ? kp : nullptr, h->ncell, host);
+        auto de = st.out(h, 3, eta, h->ncell, host, false);
+        if (!dS[0] || !dS[1] || !de[0] || !de[1] || !de[2])
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_elasticity: null vector");
+        launch_estimate_elasticity(h, dS.data(), sigma_h ? dH.data() : nullptr, fh ? df.data() : nullptr, dk[0], pi_1, de.data());
+        if (host)
+          Staged::back(h, 3, eta, de, h->ncell);
+      });
+}
 } // extern "C"

@@ -199,11 +199,18 @@ struct eqlb_handle
   TableView tv{};
   std::vector<double> h_tables_q;  // quadrature style tables needed by the projector (dg_q, qwts)
   DevBuf<double> d_proj;           // [ndg][nq] projection operator (mass^-1 * dg_q^T * w)
+  DevBuf<double> d_primal;         // primal-space / estimator tables (offsets o_pr, see eqlb_create)
+  int o_pr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int npk = 0;
+  DevBuf<int32_t> d_pk_dofmap;     // [ncell][npk] cell dofmap of the primal P_k space (eqlb_set_primal_space)
+  int64_t pk_ndofs = 0;
+  DevBuf<double> d_basix;          // [k][k] + [(k*k-k)][nrt] hierarchic RT -> Basix RT (Legendre) maps
 
   // boundary data
   DevBuf<int8_t> d_facet_type;  // [nrhs][nfct]
   DevBuf<double> d_bflux;       // [nrhs][ncell*nrt] (zeros where absent)
   std::vector<uint8_t> h_has_bflux;
+  bool bflux_dummy = false;  // no flux-BC facet at all: d_bflux is a 2-element placeholder (never dereferenced)
   DevBuf<int8_t> d_node_on_bnd;
   DevBuf<int8_t> d_local_fct_id;  // [nfct] cell-local id of the flux-BC facets
 
@@ -267,6 +274,13 @@ void launch_bc_poly(eqlb_handle* h, int r, int nprime, const int32_t* d_prime, i
 void launch_bc_node_markers(eqlb_handle* h, const int32_t* d_cnt);
 int count_bad_local_fct_ids(eqlb_handle* h, const int8_t* d_lid);
 void launch_flux_norm(eqlb_handle* h, int nfun, const double* const* dsig, double* const* dout);
+void launch_primal_project(eqlb_handle* h, int nfun, const double* const* uh, const double* const* fh, double* const* G,
+                           double* const* F);
+void launch_estimate_poisson(eqlb_handle* h, int nfun, const double* const* sigma, const double* const* uh, const double* const* fh,
+                             double* const* e_sig, double* const* e_osc, int is_ev);
+void launch_estimate_elasticity(eqlb_handle* h, const double* const* ds, const double* const* sh, const double* const* fh,
+                                const double* korn, double pi_1, double* const* eta);
+void launch_ev_to_basix(eqlb_handle* h, int nfun, const double* const* din, double* const* dout);
 void build_k1_tables(eqlb_handle* h, const eqlb_tables* t);
 void launch_k1(eqlb_handle* h, bool ev, const RhsPtrs& ptrs, int first, int count, int use_atomics, int lanes, int64_t recoff,
                bool pdl);

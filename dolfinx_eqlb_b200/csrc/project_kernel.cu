@@ -141,3 +141,101 @@ void launch_project(eqlb_handle* h, int nfun, const double* const* dq, double* c
     h->launches++;
   }
 }
+
+// ---------------------------------------------------------------------------
+// EV epilogue: conforming hierarchic-RT vector -> DOF vector of the same function w.r.t. the functionals of
+// Basix' "RT" element, Legendre variant (`FluxEqlbEV.py:95`).  Facet part: k x k matrix A per facet (both sets
+// of functionals are normal moments in the global facet orientation).  Interior part: the Basix interior
+// moments of a cell are a fixed linear map B of ALL cell-local hierarchic DOFs; the cell-local facet DOFs come
+// from the global ones through the reflection matrix R (c_loc = R c_glob, R an involution).
+// Pure streaming: 8 (k + ...) B per facet / cell, HBM bound.
+// ---------------------------------------------------------------------------
+namespace
+{
+__global__ void basix_facet_kernel(int nfct, int k, const double* __restrict__ A, const double* __restrict__ in,
+                                   double* __restrict__ out)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfct)
+    return;
+  double c[4], r[4];
+  for (int j = 0; j < k; ++j)
+    c[j] = in[(size_t)f * k + j];
+  for (int i = 0; i < k; ++i)
+  {
+    double s = 0.0;
+    for (int j = 0; j < k; ++j)
+      s += A[i * k + j] * c[j];
+    r[i] = s;
+  }
+  for (int i = 0; i < k; ++i)
+    out[(size_t)f * k + i] = r[i];
+}
+
+__global__ void basix_interior_kernel(int ncell, int nfct, int k, int nrt, const double* __restrict__ B,
+                                      const double* __restrict__ trafo, const int32_t* __restrict__ cell_fct,
+                                      const uint8_t* __restrict__ fct_perms, const double* __restrict__ in,
+                                      double* __restrict__ out)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell)
+    return;
+  const int ncd = k * k - k;
+  double loc[24];
+  for (int f = 0; f < 3; ++f)
+  {
+    const int32_t gf = cell_fct[3 * (size_t)c + f];
+    double g[4];
+    for (int j = 0; j < k; ++j)
+      g[j] = in[(size_t)gf * k + j];
+    if (fct_perms[3 * (size_t)c + f])
+    {
+      // c_loc = R c_glob with R[i][j] = trafo[j][i] (trafo holds R^T, se/KernelData.cpp:55-64)
+      for (int i = 0; i < k; ++i)
+      {
+        double s = 0.0;
+        for (int j = 0; j < k; ++j)
+          s += trafo[j * k + i] * g[j];
+        loc[f * k + i] = s;
+      }
+    }
+    else
+      for (int j = 0; j < k; ++j)
+        loc[f * k + j] = g[j];
+  }
+  for (int i = 0; i < ncd; ++i)
+    loc[3 * k + i] = in[(size_t)nfct * k + (size_t)c * ncd + i];
+  for (int i = 0; i < ncd; ++i)
+  {
+    double s = 0.0;
+    for (int j = 0; j < nrt; ++j)
+      s += B[i * nrt + j] * loc[j];
+    out[(size_t)nfct * k + (size_t)c * ncd + i] = s;
+  }
+}
+} // namespace
+
+void launch_ev_to_basix(eqlb_handle* h, int nfun, const double* const* din, double* const* dout)
+{
+  if (!h->d_basix.p)
+    throw EqlbError(EQLB_ERR_STATE, "eqlb_ev_to_basix_rt: the tables carry no hierarchic -> Basix maps");
+  if (h->k > 4)
+    throw EqlbError(EQLB_ERR_INPUT, "eqlb_ev_to_basix_rt: degree > 4 not supported");
+  const int bs = 256, k = h->k;
+  const double* A = h->d_basix.p;
+  const double* B = h->d_basix.p + k * k;
+  const double* trafo = h->tv.data + h->tv.o_trafo;
+  for (int f = 0; f < nfun; ++f)
+  {
+    basix_facet_kernel<<<(h->nfct + bs - 1) / bs, bs, 0, h->stream>>>(h->nfct, k, A, din[f], dout[f]);
+    CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    if (k > 1)
+    {
+      basix_interior_kernel<<<(h->ncell + bs - 1) / bs, bs, 0, h->stream>>>(h->ncell, h->nfct, k, h->nrt, B, trafo, h->d_cell_fct.p,
+                                                                              h->d_fct_perms.p, din[f], dout[f]);
+      CUDA_CHECK(cudaGetLastError());
+      h->launches++;
+    }
+  }
+}

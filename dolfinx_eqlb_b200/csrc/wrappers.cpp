@@ -211,6 +211,7 @@ struct Tables
     t.nqf = geti("nqf");
     t.ndiv = geti("ndiv");
     t.nadd = geti("nadd");
+    t.npk = geti("npk");
     auto getd = [&](const char* n) -> const double*
     {
       darray a = darray::ensure(obj.attr(n));
@@ -248,6 +249,14 @@ struct Tables
     t.dg_mono = getd("dg_mono");
     t.hat_dg_rt = getd("hat_dg_rt");
     t.mono_int = getd("mono_int");
+    t.rt_basix_fct = getd("rt_basix_fct");
+    t.rt_basix_int = getd("rt_basix_int");
+    t.pk_grad_dg = getd("pk_grad_dg");
+    t.pk_to_dg = getd("pk_to_dg");
+    t.pk_q = getd("pk_q");
+    t.pk_gq = getd("pk_gq");
+    t.pk_hq = getd("pk_hq");
+    t.rt_div_q = getd("rt_div_q");
   }
 };
 

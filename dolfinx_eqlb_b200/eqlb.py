@@ -190,6 +190,59 @@ class _Problem:
         bd.num_rhs = self.nrhs
         return bd
 
+    # ---- fused input stage and error estimator ----
+    def set_primal_space(self, pk_dofmap, ndofs):
+        """Cell dofmap [ncell][npk] of the continuous P_k space of the primal solution (Basix DOF order)."""
+        dm = np.ascontiguousarray(pk_dofmap, dtype=np.int32)
+        if dm.shape != (self.mesh.ncell, self.tables.npk):
+            raise RuntimeError("set_primal_space: dofmap must be [ncell][npk]")
+        self.pk_ndofs = int(ndofs)
+        _check(self.lib, self.lib.eqlb_set_primal_space(self.h, dm.ctypes.data_as(cabi.c_int32_p), int(ndofs)))
+
+    def project_primal(self, uh=None, fh=None):
+        """`lsolver/projection.py:17-77` on the device: (G, F) = (Pi(-grad u_h), Pi f_h) from P_k coefficient vectors."""
+        n = len(uh) if uh is not None else len(fh)
+        T, m = self.tables, self.mesh
+        G = [np.zeros(m.ncell * T.ndg * 2) for _ in range(n)] if uh is not None else None
+        F = [np.zeros(m.ncell * T.ndg) for _ in range(n)] if fh is not None else None
+        pa = lambda xs: cabi.ptr_array(_as_ptr_list(xs)) if xs is not None else C.POINTER(cabi.c_double_p)()
+        keep = (_as_ptr_list(uh) if uh is not None else None, _as_ptr_list(fh) if fh is not None else None)
+        _check(self.lib, self.lib.eqlb_project_primal(
+            self.h, n, cabi.ptr_array(keep[0]) if keep[0] is not None else C.POINTER(cabi.c_double_p)(),
+            cabi.ptr_array(keep[1]) if keep[1] is not None else C.POINTER(cabi.c_double_p)(),
+            cabi.ptr_array(G) if G is not None else C.POINTER(cabi.c_double_p)(),
+            cabi.ptr_array(F) if F is not None else C.POINTER(cabi.c_double_p)(), 0))
+        return G, F
+
+    def run_primal(self, ev, uh, fh, sigma, korn=None, zeroed=False):
+        """projection + equilibration in one call (`eqlb_ev_run_primal` / `eqlb_se_run_primal`), host vectors"""
+        u, f = _as_ptr_list(uh), _as_ptr_list(fh)
+        ms = 2 if zeroed else 0
+        if ev:
+            _check(self.lib, self.lib.eqlb_ev_run_primal(self.h, cabi.ptr_array(u), cabi.ptr_array(f), cabi.ptr_array(sigma), ms))
+        else:
+            kp = korn.ctypes.data_as(cabi.c_double_p) if korn is not None else cabi.c_double_p()
+            _check(self.lib, self.lib.eqlb_se_run_primal(self.h, cabi.ptr_array(u), cabi.ptr_array(f), cabi.ptr_array(sigma), kp, ms))
+
+    def estimate_poisson(self, sigma, uh, fh, is_ev):
+        """cell-wise (eta_sig^2, eta_osc^2) of `demo/poisson/demo_error_estimation.py:52-122` on the device"""
+        n = len(sigma)
+        s, u, f = _as_ptr_list(sigma), _as_ptr_list(uh), _as_ptr_list(fh)
+        e1 = [np.zeros(self.mesh.ncell) for _ in range(n)]
+        e2 = [np.zeros(self.mesh.ncell) for _ in range(n)]
+        _check(self.lib, self.lib.eqlb_estimate_poisson(self.h, n, cabi.ptr_array(s), cabi.ptr_array(u), cabi.ptr_array(f),
+                                                        cabi.ptr_array(e1), cabi.ptr_array(e2), int(bool(is_ev)), 0))
+        return e1, e2
+
+    def estimate_elasticity(self, dsig, sigma_h, fh, korn, pi_1):
+        """cell-wise indicators of `demo/elasticity/demo_error_estimation.py:49-135` (displacement formulation)"""
+        s, sh, f = _as_ptr_list(dsig), _as_ptr_list(sigma_h), _as_ptr_list(fh)
+        kc = np.ascontiguousarray(korn, dtype=np.float64)
+        eta = [np.zeros(self.mesh.ncell) for _ in range(3)]
+        _check(self.lib, self.lib.eqlb_estimate_elasticity(self.h, cabi.ptr_array(s), cabi.ptr_array(sh), cabi.ptr_array(f),
+                                                           kc.ctypes.data_as(cabi.c_double_p), float(pi_1), cabi.ptr_array(eta), 0))
+        return eta
+
     def launch_count(self):
         return int(self.lib.eqlb_launch_count(self.h))
 
@@ -420,6 +473,14 @@ class FluxEqlbEV(FluxEquilibrator):
     def equilibrate_fluxes(self):
         reconstruct_fluxes_minimisation(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, zeroed=self._fresh)
         self._fresh = False
+
+    def fluxes_in_basix_rt(self):
+        """The equilibrated fluxes as DOF vectors of Basix' "RT" element (Legendre variant) - the space the
+        reference's FluxEqlbEV returns (`FluxEqlbEV.py:95`); layout [facet dofs nfct*k][cell dofs] (`eqlb_ev_to_basix_rt`)."""
+        out = [np.zeros(self.ndofs) for _ in range(self.n_fluxes)]
+        _check(self.problem.lib, self.problem.lib.eqlb_ev_to_basix_rt(self.problem.h, self.n_fluxes, cabi.ptr_array(self.list_flux),
+                                                                      cabi.ptr_array(out), 0))
+        return out
 
 
 def local_projection(problem: _Problem, qvals):

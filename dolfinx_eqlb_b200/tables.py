@@ -339,7 +339,83 @@ class Tables:
     dg_mono: np.ndarray = None  # [1+ndiv][ndg]       int psi_i x^l y^m
     hat_dg_rt: np.ndarray = None  # [3 v][ndg][nrt][2]  int lam_v psi_m phi_i^d
     mono_int: np.ndarray = None  # [1+ndiv]            int x^l y^m
+    # primal space P_k (continuous Lagrange, Basix DOF order) for the fused input stage and the error estimator
+    npk: int = 0
+    pk_grad_dg: np.ndarray = None  # [ndg][npk][2]  reference gradient of the P_k basis at the DG_p nodes
+    pk_to_dg: np.ndarray = None  # [ndg][npk]      L2 projection P_k -> DG_p on the reference cell
+    pk_q: np.ndarray = None  # [nq][npk]       P_k basis at the cell quadrature points
+    pk_gq: np.ndarray = None  # [nq][npk][2]    reference gradient
+    pk_hq: np.ndarray = None  # [nq][npk][3]    reference second derivatives xx, xy, yy
+    rt_div_q: np.ndarray = None  # [nq][nrt]       reference divergence of the RT basis
+    # change of basis hierarchic RT -> Basix "RT" (Legendre variant), see basix_rt_legendre_maps
+    rt_basix_fct: np.ndarray = None  # [k][k]        facet dofs:    c_basix = A c_hier (global facet orientation)
+    rt_basix_int: np.ndarray = None  # [k*k-k][nrt]  interior dofs: c_basix = B c_hier (cell-local dofs)
     extra: dict = field(default_factory=dict)
+
+
+def dubiner_basis(n):
+    """Orthonormal polynomials of degree <= n on the reference triangle in Basix' polyset order
+    idx(p, q) = (p+q)(p+q+1)/2 + q (Dubiner basis: P_{p,q} has x-degree p, leading coefficient > 0), as
+    (exact polynomial, squared norm) pairs: Gram-Schmidt over x^p y^q, degree by degree, q descending."""
+    out = {}
+    done = []
+    for deg in range(n + 1):
+        for q in range(deg, -1, -1):
+            pdeg = deg - q
+            f = {(pdeg, q): Fr(1)}
+            for g, gg in done:
+                c = p_int_cell(p_mul(f, g)) / gg
+                f = p_add(f, g, -c)
+            gg = p_int_cell(p_mul(f, f))
+            done.append((f, gg))
+            out[(deg * (deg + 1)) // 2 + q] = (f, gg)
+    return [out[i] for i in range(len(out))]
+
+
+def legendre_01(n):
+    """Legendre polynomials P_j(2s-1), j < n, on [0, 1] as exact univariate polynomials with their squared norms
+    1/(2j+1) (Basix' orthonormal facet basis is sqrt(2j+1) P_j(2s-1))."""
+    polys = []
+    for j in range(n):
+        f = {j: Fr(1)}
+        for g, gg in polys:
+            c = u_int01(u_mul(f, g)) / gg
+            for kk, v in g.items():
+                f[kk] = f.get(kk, Fr(0)) - c * v
+        # normalise to P_j(1) = 1
+        v1 = sum(f.values(), Fr(0))
+        f = {kk: v / v1 for kk, v in f.items() if v != 0}
+        polys.append((f, u_int01(u_mul(f, f))))
+    return polys
+
+
+def basix_rt_legendre_maps(k, rt):
+    """Change of basis from the hierarchic RT_k element to Basix' "RT" element with the Legendre variant - the
+    space `FluxEqlbEV` creates (`python/dolfinx_eqlb/eqlb/FluxEqlbEV.py:95`, `ufl.FiniteElement("RT", cell, k)`;
+    Basix 0.6 `create_rt`: facet DOFs = normal moments against the orthonormal Legendre basis of P_{k-1} on the
+    facet, interior DOFs = moments against the orthonormal basis of (P_{k-2})^2, direction-major).  Basix is third
+    party and absent here: the functionals are restated from its definition (PARITY UNPINNED against a Basix
+    install; for k >= 3 the ordering of the interior moments is the part that could differ).  The DOF vector of the
+    same function is c_basix = L_basix(phi_hier) c_hier:
+        A[i][j]  = coefficient of the facet moment int v.n s^j in the Legendre moment i     (k x k)
+        B[i][j]  = L^basix_int,i(phi^hier_j)                                            ((k^2-k) x nrt)"""
+    leg = legendre_01(k)
+    A = np.zeros((k, k))
+    for i, (f, gg) in enumerate(leg):
+        nrm = float(gg) ** -0.5
+        for j, c in f.items():
+            A[i, j] = float(c) * nrm
+    ncd = k * k - k
+    B = np.zeros((ncd, len(rt)))
+    if k > 1:
+        dub = dubiner_basis(k - 2)
+        nsc = len(dub)
+        for d in range(2):
+            for i, (q, gg) in enumerate(dub):
+                nrm = float(gg) ** -0.5
+                for j, (px, py) in enumerate(rt):
+                    B[d * nsc + i, j] = float(p_int_cell(p_mul(q, px if d == 0 else py))) * nrm
+    return A, B
 
 
 _CACHE: dict = {}
@@ -491,6 +567,46 @@ def make_tables(k: int, p: int | None = None) -> Tables:
                 hdr[v, m_, i, 1] = float(p_int_cell(p_mul(w, rt[i][1])))
     T.hat_dg_rt = hdr
 
+    T.rt_basix_fct, T.rt_basix_int = basix_rt_legendre_maps(k, rt)
+
+    # ---- primal space P_k: fused projection (`lsolver/projection.py:17-77` for G = Pi(-grad u_h), Pi f_h) and
+    # error estimator (`demo/poisson/demo_error_estimation.py:52-122`) ----
+    pk = lagrange_basis(k)
+    npk = len(pk)
+    T.npk = npk
+    dgn = lagrange_nodes(p)
+    gdg = np.zeros((ndg, npk, 2))
+    for j, ph in enumerate(pk):
+        phx, phy = p_dx(ph), p_dy(ph)
+        for i, (xn, yn) in enumerate(dgn):
+            gdg[i, j, 0] = p_eval(phx, xn, yn)
+            gdg[i, j, 1] = p_eval(phy, xn, yn)
+    T.pk_grad_dg = gdg
+    # L2 projection P_k -> DG_p: M_dg^-1 (psi_i, phi_j), exact
+    Mdg = [[p_int_cell(p_mul(a, b)) for b in dg] for a in dg]
+    Cx = [[p_int_cell(p_mul(a, b)) for b in pk] for a in dg]
+    Pj = solve_exact(Mdg, Cx)
+    T.pk_to_dg = np.array([[float(v) for v in row] for row in Pj])
+    pkq = np.zeros((nq, npk))
+    pkg = np.zeros((nq, npk, 2))
+    pkh = np.zeros((nq, npk, 3))
+    for j, ph in enumerate(pk):
+        phx, phy = p_dx(ph), p_dy(ph)
+        hxx, hxy, hyy = p_dx(phx), p_dy(phx), p_dy(phy)
+        for n_, (x, y) in enumerate(qpts):
+            pkq[n_, j] = p_eval(ph, x, y)
+            pkg[n_, j, 0] = p_eval(phx, x, y)
+            pkg[n_, j, 1] = p_eval(phy, x, y)
+            pkh[n_, j, 0] = p_eval(hxx, x, y)
+            pkh[n_, j, 1] = p_eval(hxy, x, y)
+            pkh[n_, j, 2] = p_eval(hyy, x, y)
+    T.pk_q, T.pk_gq, T.pk_hq = pkq, pkg, pkh
+    rdq = np.zeros((nq, nrt))
+    for i, (px, py) in enumerate(rt):
+        dv = p_add(p_dx(px), p_dy(py))
+        for n_, (x, y) in enumerate(qpts):
+            rdq[n_, i] = p_eval(dv, x, y)
+    T.rt_div_q = rdq
     T.extra["rt_exact"] = rt
     T.extra["dg_exact"] = dg
     T.extra["fpts"] = fpts

@@ -92,13 +92,21 @@ typedef struct eqlb_mesh {
 /* Reference-element tables (dolfinx_eqlb_b200/tables.py; Basix-derived in a
  * DOLFINx deployment).  HOST pointers. Shapes in tables.py::Tables. */
 typedef struct eqlb_tables {
-  int32_t k, p, nrt, ndg, ndg_fct, nq, nqf, ndiv, nadd;
+  int32_t k, p, nrt, ndg, ndg_fct, nq, nqf, ndiv, nadd, npk;
   /* quadrature-style tables (what se::KernelData holds) */
   const double *qpts, *qwts, *fpts_s, *fwts, *M, *rt_q, *rt_f, *dg_q, *dg_f, *hat_q, *hat_f, *trafo;
   const int32_t *fct_closure, *div_lm;
   /* reference-matrix tables (exact integrals on the reference cell) */
   const double *rt_mass, *fct_mom, *cell_mom_f, *cell_mom_g, *bc_mat, *rt_p1;
   const double *dg_mono, *hat_dg_rt, *mono_int; /* EV load vector / divergence data */
+  /* change of basis hierarchic RT -> Basix "RT" (Legendre variant): [k][k] facet part, [(k*k-k)][nrt]
+   * interior part (tables.py::basix_rt_legendre_maps); may be NULL (eqlb_ev_to_basix_rt then fails) */
+  const double *rt_basix_fct, *rt_basix_int;
+  /* primal space P_k (npk dofs per cell, Basix order) for eqlb_set_primal_space / eqlb_*_run_primal /
+   * eqlb_estimate_*: gradients at the DG_p nodes [ndg][npk][2], L2 projection P_k -> DG_p [ndg][npk], basis /
+   * gradient / second derivatives at the cell quadrature points [nq][npk](x2, x3), divergence of the RT basis at
+   * the quadrature points [nq][nrt]; may be NULL (those entry points then fail) */
+  const double *pk_grad_dg, *pk_to_dg, *pk_q, *pk_gq, *pk_hq, *rt_div_q;
 } eqlb_tables;
 
 typedef struct eqlb_handle eqlb_handle;
@@ -167,6 +175,46 @@ int eqlb_se_run(eqlb_handle* h, const double* const* G, const double* const* f,
  * ACCUMULATED (`ev/solve_patch.hpp:216-227`). */
 int eqlb_ev_run(eqlb_handle* h, const double* const* G, const double* const* f,
                 double* const* sigma, int memspace);
+
+/* EV output in the space the reference's FluxEqlbEV returns (`python/dolfinx_eqlb/eqlb/FluxEqlbEV.py:95`:
+ * Basix "RT", Legendre variant): converts conforming hierarchic-RT vectors (layout of eqlb_ev_run) into the
+ * DOF vectors of the SAME functions w.r.t. the Basix functionals, same layout [facet dofs nfct*k (facets in
+ * their global low->high vertex orientation)][cell dofs ncell*(k*k-k)]; a DOLFINx binding scatters them
+ * through `V_flux.dofmap`.  in == out allowed only for different buffers (out of place).
+ * The Basix functionals are restated from Basix' definition (third party, not in the reference tree):
+ * see tables.py::basix_rt_legendre_maps for what is and is not pinned. */
+int eqlb_ev_to_basix_rt(eqlb_handle* h, int nfun, const double* const* sigma_hier, double* const* sigma_basix, int memspace);
+
+/* ---- fused input stage and error estimator ----
+ * eqlb_set_primal_space: the continuous P_k space of the primal solution (k = flux degree): cell dofmap
+ *   [ncell*npk] (Basix DOF order: vertices, edge interiors, cell interior; HOST pointer, copied) and its size.
+ * eqlb_project_primal: what `lsolver/projection.py:17-77` computes before the equilibration, on the device:
+ *   G[r] = Pi_{DG_p}(-grad u_h[r]) (exact: grad u_h is piecewise P_{k-1}), F[r] = Pi_{DG_p} f_h[r], both from P_k
+ *   coefficient vectors; writes the [ncell*ndg*2] / [ncell*ndg] arrays eqlb_se_run / eqlb_ev_run take.
+ *   Any of uh / fh (and the matching output) may be NULL.
+ * eqlb_ev_run_primal / eqlb_se_run_primal: projection + equilibration in one call; host callers move the two P_k
+ *   vectors (8 B per primal dof) instead of G and F (24 ndg B per cell): the host->device volume of an EV degree-2
+ *   call at 1024^2 drops from 302 MB to 134 MB.
+ * eqlb_estimate_poisson: cell-wise error indicators of `python/demo/poisson/demo_error_estimation.py:52-122`
+ *   eta_sig2[c] = ||sigma_eqlb||^2_T (semi-explicit, discontinuous flux) or ||grad u_h + sigma_eqlb||^2_T (conforming)
+ *   eta_osc2[c] = (h_T/pi)^2 ||f_h - div sigma||^2_T, sigma = sigma_eqlb - grad u_h (SE) or sigma_eqlb (EV)
+ *   sigma: DRT vector (is_ev = 0) or conforming hierarchic-RT vector (is_ev = 1); only 2 * ncell doubles per
+ *   function go back to the host instead of the flux vector.
+ * eqlb_estimate_elasticity: `python/demo/elasticity/demo_error_estimation.py:49-135`, displacement formulation:
+ *   eta[0][c] = int dsig : a(dsig), a(s) = (s - pi_1/(2+2 pi_1) tr(s) I)/2;  eta[1][c] = int (c_K (dsig_01 - dsig_10)/2)^2;
+ *   eta[2][c] = (c_K h_T/pi)^2 ||f_h + div(sigma_h + dsig)||^2_T; dsig rows = DRT vectors, sigma_h rows = DG_p^2 vectors
+ *   (the projected stress handed to the equilibration as -G), f_h rows = P_k vectors, korn = cell-wise c_K.
+ * memspace: EQLB_HOST or EQLB_DEVICE for all data pointers of a call. */
+int eqlb_set_primal_space(eqlb_handle* h, const int32_t* pk_dofmap, int64_t ndofs);
+int eqlb_project_primal(eqlb_handle* h, int nfun, const double* const* uh, const double* const* fh, double* const* G,
+                        double* const* F, int memspace);
+int eqlb_ev_run_primal(eqlb_handle* h, const double* const* uh, const double* const* fh, double* const* sigma, int memspace);
+int eqlb_se_run_primal(eqlb_handle* h, const double* const* uh, const double* const* fh, double* const* sigma, double* korn,
+                       int memspace);
+int eqlb_estimate_poisson(eqlb_handle* h, int nfun, const double* const* sigma, const double* const* uh,
+                          const double* const* fh, double* const* eta_sig2, double* const* eta_osc2, int is_ev, int memspace);
+int eqlb_estimate_elasticity(eqlb_handle* h, const double* const* dsig, const double* const* sigma_h, const double* const* fh,
+                             const double* korn, double pi_1, double* const* eta, int memspace);
 
 /* Cell-wise L2 projection into DG_p (the fixed-form fast path of
  * `base::local_solver_cholesky`, `base/local_solver.hpp:38-187`, as used by

@@ -393,6 +393,8 @@ def halo_check(args, rank, world, dist_mod):
         err = max(err, float(d.max() / max(np.abs(want).max(), 1e-300)))
     t = torch.tensor([err], device="cuda", dtype=torch.float64)
     dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    if hasattr(hx, "close"):
+        hx.close()
     del hx
     return float(t.item())
 
@@ -628,6 +630,54 @@ def main():
     h2d = sum(g.numel() * 8 for g in hG) + sum(f.numel() * 8 for f in hF)
     d2h = sum(s.numel() * 8 for s in hS)
 
+    # ---- fused call (SURVEY 8f ranks 2+3): the primal solution u_h and the data f_h (P_k vectors) go in, the
+    # projection, the equilibration and the error estimator run on the device, the cell-wise indicators come back
+    fused = None
+    if world == 1 and not args.stress and k <= 3:
+        from dolfinx_eqlb_b200 import mesh as ms_
+
+        dm, npk_dofs = ms_.pk_dofmap(m, k)
+        hprob.set_primal_space(dm, npk_dofs)
+        rngf = np.random.default_rng(SEED + 3)
+        hU = [torch.from_numpy(rngf.standard_normal(npk_dofs)).pin_memory() for _ in range(nrhs)]
+        hFh = [torch.from_numpy(rngf.standard_normal(npk_dofs)).pin_memory() for _ in range(nrhs)]
+        hE1 = [torch.zeros(m.ncell, dtype=torch.float64).pin_memory() for _ in range(nrhs)]
+        hE2 = [torch.zeros(m.ncell, dtype=torch.float64).pin_memory() for _ in range(nrhs)]
+        dU = [torch.empty(npk_dofs, dtype=torch.float64, device="cuda") for _ in range(nrhs)]
+        dFh = [torch.empty(npk_dofs, dtype=torch.float64, device="cuda") for _ in range(nrhs)]
+        dE1 = [torch.empty(m.ncell, dtype=torch.float64, device="cuda") for _ in range(nrhs)]
+        dE2 = [torch.empty(m.ncell, dtype=torch.float64, device="cuda") for _ in range(nrhs)]
+        pU, pFh, pE1, pE2 = dptrs(dU), dptrs(dFh), dptrs(dE1), dptrs(dE2)
+        is_ev = args.path == "ev"
+
+        def step_fused():
+            for d, h_ in zip(dU + dFh, hU + hFh):
+                d.copy_(h_, non_blocking=True)
+            for d in dS:
+                d.zero_()
+            if is_ev:
+                rc = lib.eqlb_ev_run_primal(hprob.h, pU, pFh, pS, 1)
+            else:
+                rc = lib.eqlb_se_run_primal(hprob.h, pU, pFh, pS, cabi.c_double_p(), 1)
+            if rc == 0:
+                rc = lib.eqlb_estimate_poisson(hprob.h, nrhs, pS, pU, pFh, pE1, pE2, int(is_ev), 1)
+            if rc != 0:
+                raise RuntimeError(lib.eqlb_last_error().decode())
+            for d, h_ in zip(dE1 + dE2, hE1 + hE2):
+                h_.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+
+        step_fused()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_fused()
+        dtf = (time.perf_counter() - t0) / e2e_steps
+        fused = {"value": npatch_total / dtf, "unit": "patches/s", "seconds": dtf,
+                 "h2d_bytes_per_step": sum(t.numel() * 8 for t in hU + hFh), "d2h_bytes_per_step": sum(t.numel() * 8 for t in hE1 + hE2),
+                 "what": "u_h, f_h (P_k vectors, pinned host) -> device: projection + equilibration + Poisson error estimator -> "
+                         "cell-wise eta_sig^2, eta_osc^2 back to the host (the flux stays on the device)"}
+
     # ---- cold call: what one equilibration of a NEW mesh costs (adaptive loops equilibrate every mesh once):
     # eqlb_create (mesh upload, Jacobians, colouring) + eqlb_set_bcs (device patch builder) + one host-buffer call
     cold = None
@@ -652,6 +702,10 @@ def main():
 
     hcheck = None
     if dist is not None:
+        if hasattr(hx, "status"):
+            hx.status()
+        if hasattr(hx, "close"):
+            hx.close()
         del hx
         torch.cuda.synchronize()
         dist.barrier()
@@ -707,7 +761,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling_mode(args), "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
         "e2e": {"value": npatch_total / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "e2e_cold": cold, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "halo_check": hcheck, "halo": halo_name,
+        "e2e_fused": fused, "e2e_cold": cold, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "halo_check": hcheck, "halo": halo_name,
         # one-time cost per (mesh, BC set), outside the timed region: the reference redoes this work in every call
         # (second handle of the process = the staged host-call one: CUDA context and allocator are warm)
         "setup": {"eqlb_create_ms": 1e3 * hprob.create_seconds, "eqlb_set_bcs_ms": 1e3 * hprob.set_bcs_seconds,

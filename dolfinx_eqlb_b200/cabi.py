@@ -181,6 +181,8 @@ def load_library():
     lib.eqlb_halo_connect.restype = C.c_int
     lib.eqlb_halo_apply.argtypes = [H, C.POINTER(c_double_p), C.c_int, C.c_void_p]
     lib.eqlb_halo_apply.restype = C.c_int
+    lib.eqlb_halo_status.argtypes = [H, C.c_void_p]
+    lib.eqlb_halo_status.restype = C.c_int
     lib.eqlb_halo_destroy.argtypes = [H]
     lib.eqlb_halo_destroy.restype = None
     lib.eqlb_launch_count.argtypes = [H]

@@ -656,6 +656,8 @@ int eqlb_set_bcs(eqlb_handle* h, const int8_t* facet_type, const double* const* 
       {
         if (!h || !facet_type)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs: null argument");
+        // queued patch kernels (EQLB_DEVICE calls return without synchronising) may still read the boundary data
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
         StageTimer tm;
         const size_t nf = h->nfct;
         // every boundary facet has to be classified for every RHS (se/Patch.cpp:464-470)
@@ -695,6 +697,7 @@ int eqlb_set_bcs_poly(eqlb_handle* h, const int32_t* nprime, const int32_t* cons
       {
         if (!h || !nprime || !prime_facets || !nbc)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_set_bcs_poly: null argument");
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
         StageTimer tm;
         const size_t nf = h->nfct, nb = (size_t)h->ncell * h->nrt;
         const bool stress = (h->flags & EQLB_FLAG_STRESS) != 0;
@@ -1005,6 +1008,12 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
     throw EqlbError(EQLB_ERR_STATE, std::string(who) + ": call eqlb_set_bcs first");
   if (memspace != EQLB_HOST && memspace != EQLB_DEVICE && memspace != EQLB_HOST_ZEROED && memspace != EQLB_HOST_IN)
     throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": unknown memspace");
+  for (int r = 0; r < h->nrhs; ++r)
+    if (!G[r] || !f[r] || !sigma[r])
+      throw EqlbError(EQLB_ERR_INPUT, "Equilibration: Input sizes does not match");
+  // Korn constants of a partitioned run are partial sums on halo cells and are not exchanged: all patches only
+  if (korn && h->part != EQLB_PART_ALL)
+    throw EqlbError(EQLB_ERR_INPUT, std::string(who) + ": Korn constants need EQLB_PART_ALL");
   const int nrhs = h->nrhs;
   const size_t nG = (size_t)h->ncell * h->ndg * 2, nF = (size_t)h->ncell * h->ndg;
   const size_t nS = ev ? (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k) : (size_t)h->ncell * h->nrt;

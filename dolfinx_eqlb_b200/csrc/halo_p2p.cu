@@ -31,9 +31,9 @@ struct eqlb_halo
   size_t send_off[EQLB_HALO_MAXNEIGH];      // byte offset of the send area for neighbour n in the OWN buffer
   size_t peer_send_off[EQLB_HALO_MAXNEIGH]; // byte offset of the area addressed to this rank in neighbour n's buffer
   int peer_slot[EQLB_HALO_MAXNEIGH];        // flag slot this rank owns in neighbour n's buffer
-  char* peer_buf[EQLB_HALO_MAXNEIGH];       // mapped neighbour buffers
+  char* peer_buf[EQLB_HALO_MAXNEIGH] = {};  // mapped neighbour buffers (null until eqlb_halo_connect)
   DevBuf<int64_t> idx[EQLB_HALO_MAXNEIGH];  // local DOF indices shared with neighbour n (ordered by global id)
-  DevBuf<unsigned long long> done;          // CTA counter of the pack phase (monotone over launches)
+  DevBuf<unsigned long long> done;          // [0] CTA counter of the barriers (monotone over launches), [1] error word
   int grid = 1;                             // fixed launch grid
   ~eqlb_halo()
   {
@@ -60,6 +60,11 @@ struct HaloArgs
   unsigned long long* peer_flag[EQLB_HALO_MAXNEIGH];     // flag slot in the neighbour's buffer
   const unsigned long long* my_flag[EQLB_HALO_MAXNEIGH]; // flag slot the neighbour writes in the own buffer
 };
+
+// Spins are bounded: a neighbour that never arrives (it failed, or its process died) must not hang this GPU.
+// After about 4 s (clock64 at ~2 GHz) the waiting thread records the error in done[1] and carries on; the
+// result of that exchange is then incomplete and eqlb_halo_status reports it.
+constexpr long long EQLB_HALO_SPIN_CYCLES = 8000000000ll;
 
 __global__ void __launch_bounds__(256) halo_push_add_kernel(HaloArgs a, unsigned long long* done)
 {
@@ -98,8 +103,16 @@ __global__ void __launch_bounds__(256) halo_push_add_kernel(HaloArgs a, unsigned
       else
       {
         const volatile unsigned long long* dn = done;
+        const long long t0 = clock64();
         while (*dn < target)
+        {
           __nanosleep(50);
+          if (clock64() - t0 > EQLB_HALO_SPIN_CYCLES)
+          {
+            atomicMax(done + 1, 1ull);  // grid barrier timed out (grid not co-resident?)
+            break;
+          }
+        }
       }
     }
     __syncthreads();
@@ -113,8 +126,16 @@ __global__ void __launch_bounds__(256) halo_push_add_kernel(HaloArgs a, unsigned
     if (threadIdx.x == 0)
     {
       const volatile unsigned long long* f = a.my_flag[n];
+      const long long t0 = clock64();
       while (*f < a.epoch)
+      {
         __nanosleep(100);
+        if (clock64() - t0 > EQLB_HALO_SPIN_CYCLES)
+        {
+          atomicMax(done + 1, 2ull);  // neighbour n never published this epoch
+          break;
+        }
+      }
       __threadfence_system();
     }
     __syncthreads();
@@ -159,8 +180,8 @@ int eqlb_halo_create(int nneigh, const int64_t* counts, const int64_t* const* id
     h->buf_bytes = std::max<size_t>(off, 256);
     CUDA_CHECK(cudaMalloc(&h->buf, h->buf_bytes));
     CUDA_CHECK(cudaMemset(h->buf, 0, h->buf_bytes));
-    h->done.alloc(1);
-    CUDA_CHECK(cudaMemset(h->done.p, 0, sizeof(unsigned long long)));
+    h->done.alloc(2);
+    CUDA_CHECK(cudaMemset(h->done.p, 0, 2 * sizeof(unsigned long long)));
     {
       int64_t maxc = 0;
       for (int n = 0; n < nneigh; ++n)
@@ -168,7 +189,14 @@ int eqlb_halo_create(int nneigh, const int64_t* counts, const int64_t* const* id
       int nsm = 148, dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-      h->grid = (int)std::max<int64_t>(1, std::min<int64_t>((maxc + 255) / 256, nsm));
+      // the grid barrier needs every CTA resident at once: cooperative launch, grid bounded by the occupancy
+      int per_sm = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, halo_push_add_kernel, 256, 0));
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      if (!coop || per_sm < 1)
+        throw EqlbError(EQLB_ERR_CUDA, "eqlb_halo_create: device cannot launch the halo kernel cooperatively");
+      h->grid = (int)std::max<int64_t>(1, std::min<int64_t>((maxc + 255) / 256, (int64_t)nsm * std::min(per_sm, 1)));
     }
     cudaIpcMemHandle_t ipc;
     CUDA_CHECK(cudaIpcGetMemHandle(&ipc, h->buf));
@@ -182,6 +210,11 @@ int eqlb_halo_create(int nneigh, const int64_t* counts, const int64_t* const* id
   {
     eqlb_set_error(e.what());
     return e.code;
+  }
+  catch (const std::exception& e)
+  {
+    eqlb_set_error(e.what());
+    return EQLB_ERR_CUDA;
   }
 }
 
@@ -205,6 +238,11 @@ int eqlb_halo_connect(eqlb_halo* h, int n, const unsigned char* peer_ipc_handle 
     eqlb_set_error(e.what());
     return e.code;
   }
+  catch (const std::exception& e)
+  {
+    eqlb_set_error(e.what());
+    return EQLB_ERR_CUDA;
+  }
 }
 
 int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream)
@@ -218,7 +256,7 @@ int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream)
     HaloArgs a{};
     a.nneigh = h->nneigh;
     a.nrhs = nrhs;
-    a.epoch = ++h->epoch;
+    a.epoch = h->epoch + 1;  // committed below, once the launch has succeeded
     const int par = (int)(a.epoch & 1);
     for (int r = 0; r < nrhs; ++r)
       a.x[r] = x[r];
@@ -234,8 +272,11 @@ int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream)
       a.peer_flag[n] = reinterpret_cast<unsigned long long*>(h->peer_buf[n]) + par * EQLB_HALO_MAXNEIGH + h->peer_slot[n];
       a.my_flag[n] = reinterpret_cast<const unsigned long long*>(h->buf) + par * EQLB_HALO_MAXNEIGH + n;
     }
-    halo_push_add_kernel<<<h->grid, 256, 0, (cudaStream_t)cuda_stream>>>(a, h->done.p);
-    CUDA_CHECK(cudaGetLastError());
+    unsigned long long* donep = h->done.p;
+    void* params[] = {&a, &donep};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)halo_push_add_kernel, dim3(h->grid), dim3(256), params, 0,
+                                           (cudaStream_t)cuda_stream));
+    h->epoch = a.epoch;
     return EQLB_OK;
   }
   catch (const EqlbError& e)
@@ -243,8 +284,42 @@ int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream)
     eqlb_set_error(e.what());
     return e.code;
   }
+  catch (const std::exception& e)
+  {
+    eqlb_set_error(e.what());
+    return EQLB_ERR_CUDA;
+  }
 }
 
+int eqlb_halo_status(eqlb_halo* h, void* cuda_stream)
+{
+  try
+  {
+    if (!h)
+      throw EqlbError(EQLB_ERR_INPUT, "eqlb_halo_status: null handle");
+    unsigned long long err = 0;
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    CUDA_CHECK(cudaMemcpy(&err, h->done.p + 1, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err == 1)
+      throw EqlbError(EQLB_ERR_CUDA, "halo exchange: grid barrier timed out (kernel not co-resident)");
+    if (err)
+      throw EqlbError(EQLB_ERR_CUDA, "halo exchange: a neighbour did not publish its values in time");
+    return EQLB_OK;
+  }
+  catch (const EqlbError& e)
+  {
+    eqlb_set_error(e.what());
+    return e.code;
+  }
+  catch (const std::exception& e)
+  {
+    eqlb_set_error(e.what());
+    return EQLB_ERR_CUDA;
+  }
+}
+
+// The caller has to make sure (collective barrier + device synchronisation on every rank) that no neighbour
+// still reads this rank's buffer: `P2PHaloExchange.close()` does.
 void eqlb_halo_destroy(eqlb_halo* h) { delete h; }
 
 } // extern "C"

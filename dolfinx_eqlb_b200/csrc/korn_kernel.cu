@@ -151,7 +151,8 @@ void launch_korn(eqlb_handle* h, double* dKorn)
     }
     return;
   }
-  for (int c = 0; c < h->nseg; ++c)
+  // the launch-segment window of eqlb_set_part applies here like in launch_se (interface / interior patches)
+  for (int c = std::max(0, h->win_lo); c < std::min(h->nseg, h->win_hi); ++c)
   {
     const int first = h->h_colour_off[c], count = h->h_colour_off[c + 1] - first;
     if (count == 0)

@@ -1256,7 +1256,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   const size_t smem = (size_t)h->tv.ndoubles * sizeof(double);
   const bool atomics = (h->flags & EQLB_FLAG_ATOMIC) != 0;
   const bool stress = !EV && (h->flags & EQLB_FLAG_STRESS) != 0 && K >= 2;
-  constexpr bool CAN_STRESS = !EV && K >= 2 && K <= 3;
+  constexpr bool CAN_STRESS = !EV && K >= 2 && K <= 4;
   auto kern = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, false> : patch_kernel<K, NDG, EQLB_NCMAX, EV, false>;
   if (stress)
   {
@@ -1370,6 +1370,15 @@ void dispatch(eqlb_handle* h, const double* const* dG, const double* const* dF, 
     break;
   case 306:
     launch_patch_t<3, 6, EV>(h, dG, dF, dSigma);
+    break;
+  case 401:
+    launch_patch_t<4, 1, EV>(h, dG, dF, dSigma);
+    break;
+  case 403:
+    launch_patch_t<4, 3, EV>(h, dG, dF, dSigma);
+    break;
+  case 406:
+    launch_patch_t<4, 6, EV>(h, dG, dF, dSigma);
     break;
   case 410:
     launch_patch_t<4, 10, EV>(h, dG, dF, dSigma);

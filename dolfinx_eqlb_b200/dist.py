@@ -294,9 +294,29 @@ class P2PHaloExchange:
         if rc != 0:
             raise RuntimeError(self.lib.eqlb_last_error().decode())
 
+    def status(self):
+        """Synchronise and raise if a device-side wait of an exchange timed out (`eqlb_halo_status`)."""
+        rc = self.lib.eqlb_halo_status(self.h, self.C.c_void_p(self.torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(self.lib.eqlb_last_error().decode())
+
+    def close(self, group=None):
+        """Collective: all ranks finish their exchanges (device synchronisation + barrier) before any rank frees
+        its communication buffer - the neighbours read it over NVLink."""
+        import torch.distributed as dist
+
+        if getattr(self, "h", None):
+            self.torch.cuda.synchronize()
+            dist.barrier(group=group)
+            self.lib.eqlb_halo_destroy(self.h)
+            self.h = None
+            dist.barrier(group=group)
+
     def __del__(self):
+        # no collectives in a finaliser: `close()` is the orderly way; this only avoids a leak
         try:
             if getattr(self, "h", None):
+                self.torch.cuda.synchronize()
                 self.lib.eqlb_halo_destroy(self.h)
                 self.h = None
         except Exception:

@@ -326,17 +326,38 @@ def _as_ptr_list(arrs):
     return [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
 
 
+def _check_inplace(vectors, size, what):
+    """Result vectors are accumulated in place by the C ABI (which carries no sizes): contiguous float64 arrays of
+    exactly the expected length, else the reference's 'Input sizes does not match'."""
+    for s in vectors:
+        if not (isinstance(s, np.ndarray) and s.dtype == np.float64 and s.flags.c_contiguous):
+            raise RuntimeError(f"{what} must be contiguous float64 arrays (accumulated in place)")
+        if s.shape != (size,):
+            raise RuntimeError("Equilibration: Input sizes does not match")
+
+
+def _check_inputs(problem, G, F):
+    m, T = problem.mesh, problem.tables
+    for g in G:
+        if g.shape != (m.ncell * T.ndg * 2,):
+            raise RuntimeError("Equilibration: Input sizes does not match")
+    for f in F:
+        if f.shape != (m.ncell * T.ndg,):
+            raise RuntimeError("Equilibration: Input sizes does not match")
+
+
 def reconstruct_fluxes_semiexplt(problem: _Problem, flux_hdiv, flux_dg, rhs_dg, korn=None, zeroed=False):
     """`cpp.reconstruct_fluxes_semiexplt[_with_kornconst]` (`wrappers.cpp:97-137`):
     host numpy vectors, accumulated in place into `flux_hdiv` (`zeroed`: the caller
     guarantees `flux_hdiv` is zero on entry, its upload is skipped)."""
     lib = problem.lib
     G, F = _as_ptr_list(flux_dg), _as_ptr_list(rhs_dg)
-    for s in flux_hdiv:
-        if not (isinstance(s, np.ndarray) and s.dtype == np.float64 and s.flags.c_contiguous):
-            raise RuntimeError("flux_hdiv must be contiguous float64 arrays (accumulated in place)")
     if not (len(G) == len(F) == len(flux_hdiv) == problem.nrhs):
         raise RuntimeError("Equilibration: Input sizes does not match")
+    _check_inplace(flux_hdiv, problem.mesh.ncell * problem.tables.nrt, "flux_hdiv")
+    _check_inputs(problem, G, F)
+    if korn is not None:
+        _check_inplace([korn], problem.mesh.ncell, "cells_kornconst")
     kp = korn.ctypes.data_as(cabi.c_double_p) if korn is not None else cabi.c_double_p()
     _check(lib, lib.eqlb_se_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), kp, 2 if zeroed else 0))
 
@@ -348,6 +369,9 @@ def reconstruct_fluxes_minimisation(problem: _Problem, flux_hdiv, flux_dg, rhs_d
     G, F = _as_ptr_list(flux_dg), _as_ptr_list(rhs_dg)
     if not (len(G) == len(F) == len(flux_hdiv) == problem.nrhs):
         raise RuntimeError("Equilibration: Input sizes does not match")
+    k = problem.tables.k
+    _check_inplace(flux_hdiv, problem.mesh.nfct * k + problem.mesh.ncell * (k * k - k), "flux_hdiv")
+    _check_inputs(problem, G, F)
     _check(lib, lib.eqlb_ev_run(problem.h, cabi.ptr_array(G), cabi.ptr_array(F), cabi.ptr_array(flux_hdiv), 2 if zeroed else 0))
 
 

@@ -256,6 +256,28 @@ def random_diagonal_square(n: int, seed: int = 3, scramble_seed: int | None = No
     return build_topology(x, tris)
 
 
+def pk_dofmap(mesh: Mesh, q: int):
+    """Cell dofmap [ncell][(q+1)(q+2)/2] of the continuous P_q space (q <= 3) in Basix' cell-local DOF order
+    (vertices, edge interiors e0 e1 e2 from the lower to the higher global vertex, cell interior), numbered
+    [vertex dofs | (q-1) per facet | interior per cell] - what `eqlb_set_primal_space` takes.  Returns (dofmap, ndofs)."""
+    if not 1 <= q <= 3:
+        raise ValueError("pk_dofmap: 1 <= q <= 3")
+    nloc = (q + 1) * (q + 2) // 2
+    ne = q - 1
+    nint = nloc - 3 - 3 * ne
+    dm = np.zeros((mesh.ncell, nloc), dtype=np.int64)
+    dm[:, :3] = mesh.cell_node
+    for f in range(3):
+        a, b = FACET_VERTS[f]
+        rev = mesh.cell_node[:, a] > mesh.cell_node[:, b]
+        for i in range(ne):
+            ii = np.where(rev, ne - 1 - i, i)
+            dm[:, 3 + f * ne + i] = mesh.nnode + mesh.cell_fct[:, f].astype(np.int64) * ne + ii
+    for i in range(nint):
+        dm[:, 3 + 3 * ne + i] = mesh.nnode + mesh.nfct * ne + np.arange(mesh.ncell) * nint + i
+    return dm.astype(np.int32), int(mesh.nnode + mesh.nfct * ne + mesh.ncell * nint)
+
+
 def dg_dofmap(ncell: int, ndg: int) -> np.ndarray:
     """Cell dofmap of a DG_p space: dof = cell * ndg + local (DOLFINx layout)."""
     return (np.arange(ncell, dtype=np.int32)[:, None] * ndg + np.arange(ndg, dtype=np.int32)[None, :]).astype(np.int32)

@@ -279,6 +279,11 @@ int eqlb_halo_create(int nneigh, const int64_t* counts, const int64_t* const* id
 int eqlb_halo_connect(eqlb_halo* h, int n, const unsigned char* peer_ipc_handle,
                       int64_t peer_send_off, int peer_slot);
 int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream);
+/* synchronises the stream and reports a timed-out exchange (all device-side waits are bounded: a neighbour that
+ * never arrives costs seconds, not a hung GPU) */
+int eqlb_halo_status(eqlb_halo* h, void* cuda_stream);
+/* every rank must have finished its exchanges (collective barrier + device synchronisation) before any rank
+ * destroys its handle: the neighbours read this rank's buffer over NVLink */
 void eqlb_halo_destroy(eqlb_halo* h);
 
 /* Cell-wise squared L2 norm of DRT_k flux functions, eta2[i][cell] = ||sigma_i||^2_{L2(cell)}:

@@ -44,7 +44,8 @@ def test_se_maps_and_flux_vs_reference(kind, n, scramble, k):
 
 @pytest.mark.parametrize("kind,n,scramble", MESHES)
 @pytest.mark.parametrize("k,nsides", [(2, []), (3, []), (2, [1]), (3, [1]), (3, [1, 2]), (3, [2, 3, 4]), (2, [1, 3]), (2, [1, 2]),
-                                      (2, [2, 3, 4]), (2, [3]), (2, [2, 4]), (3, [1, 2, 4]), (2, [1, 4]), (3, [3, 4])])
+                                      (2, [2, 3, 4]), (2, [3]), (2, [2, 4]), (3, [1, 2, 4]), (2, [1, 4]), (3, [3, 4]),
+                                      (4, []), (4, [1]), (4, [1, 2]), (4, [2, 3, 4])])  # degree 4: test_stressqlb_conditions.py:22
 def test_stress_vs_reference(kind, n, scramble, k, nsides):
     from oracle import pyoracle as po
     from test_gpu_stress import elasticity_case
@@ -91,3 +92,15 @@ def test_ev_flux_vs_reference(kind, n, scramble, hom, k, nsets):
     eq.equilibrate_fluxes()
     for r in range(case.nrhs):
         assert rel_err(eq.list_flux[r], ref[r]) < RTOL
+
+
+@pytest.mark.parametrize("k,p", [(2, 0), (3, 1), (4, 0), (4, 1), (4, 2), (4, 3)])
+def test_se_lower_degree_data_vs_reference(k, p):
+    """projected data of lower degree than k-1 (`se/reconstruction.hpp:358-369` allows p <= k-1)"""
+    m = make_mesh("crossed", 4, 3, perturb=0.2)
+    case = PoissonCase(m, k, [[1, 4]], seed=2, p=p, galerkin=False)
+    ref = pr.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    eq = eqlb.FluxEqlbSE(k, m, case.F, case.G, degree_proj=p)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    eq.equilibrate_fluxes()
+    assert rel_err(eq.list_flux[0], ref[0]) < RTOL

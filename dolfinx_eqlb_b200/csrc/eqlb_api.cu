@@ -162,27 +162,54 @@ void colour_patches(eqlb_handle* h)
     h->h_colour_off[c + 1] += h->h_colour_off[c];
   std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
   h->h_order.resize(h->nactive);
-  // within a segment: patches eligible for the streaming k=2 kernels first (interior patches,
-  // or any patch of a single-RHS problem: `reversion_required` cannot occur there)
-  auto eligible = [&](int z)
+  // within a segment: patches eligible for the lane-per-cell kernels first (interior patches, or any
+  // patch of a single-RHS problem: `reversion_required` cannot occur there; at most 16 facets), ordered
+  // by lane class 4 / 8 / 16; a class with few members joins the next wider one (saves a launch)
+  auto lane_class = [&](int z)
   {
-    return h->nrhs == 1
-           || (T.node_fct_off[z + 1] - T.node_fct_off[z]) == (T.node_cell_off[z + 1] - T.node_cell_off[z]);
+    const int nf = T.node_fct_off[z + 1] - T.node_fct_off[z], nc = T.node_cell_off[z + 1] - T.node_cell_off[z];
+    if (nf > 16 || !(h->nrhs == 1 || nf == nc))
+      return 3;
+    return nf <= 4 ? 0 : (nf <= 8 ? 1 : 2);
   };
+  std::vector<int32_t> ccount(3 * (size_t)h->nseg, 0);
+  for (int z = 0; z < n; ++z)
+    if (h->h_owned[z] && !h->h_grouped[z] && lane_class(z) < 3)
+      ccount[3 * seg_of(z) + lane_class(z)]++;
+  std::vector<int8_t> cmap(3 * (size_t)h->nseg);
+  for (int sg = 0; sg < h->nseg; ++sg)
+  {
+    int32_t* cc = &ccount[3 * sg];
+    int8_t* cm = &cmap[3 * sg];
+    cm[0] = 0, cm[1] = 1, cm[2] = 2;
+    const int thr = std::max(8192, (cc[0] + cc[1] + cc[2]) / 16);
+    if (cc[1] > 0 && cc[1] < thr && cc[2] > 0)
+      cm[1] = 2, cc[2] += cc[1], cc[1] = 0;
+    if (cc[0] > 0 && cc[0] < thr && cc[1] + cc[2] > 0)
+    {
+      cm[0] = cc[1] > 0 ? 1 : 2;
+      cc[cm[0]] += cc[0], cc[0] = 0;
+    }
+  }
   h->h_colour_fast.assign(h->nseg, 0);
-  h->h_colour_maxnf.assign(h->nseg, 0);
-  for (int pass = 0; pass < 2; ++pass)
+  h->h_seg_subs.assign(h->nseg, {});
+  for (int pass = 0; pass < 4; ++pass)
+  {
+    if (pass < 3)
+      for (int sg = 0; sg < h->nseg; ++sg)
+        if (ccount[3 * sg + pass] > 0)
+          h->h_seg_subs[sg].push_back({pos[sg], ccount[3 * sg + pass], 4 << pass, -1});
     for (int z = 0; z < n; ++z)
-      if (h->h_owned[z] && !h->h_grouped[z] && eligible(z) == (pass == 0))
+      if (h->h_owned[z] && !h->h_grouped[z])
       {
-        const int sg = seg_of(z);
+        const int lc = lane_class(z), sg = seg_of(z);
+        if ((lc < 3 ? cmap[3 * sg + lc] : 3) != pass)
+          continue;
         h->h_order[pos[sg]++] = z;
-        if (pass == 0)
-        {
+        if (pass < 3)
           h->h_colour_fast[sg]++;
-          h->h_colour_maxnf[sg] = std::max(h->h_colour_maxnf[sg], T.node_fct_off[z + 1] - T.node_fct_off[z]);
-        }
       }
+  }
 
   // result ranges of the host pipeline: a range of DOFs can go back to the host after the
   // last stage with a patch that adds into it
@@ -330,25 +357,18 @@ static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* n
     {
       // lane records: S lanes per patch for the eligible head of every segment, each
       // segment padded to a whole number of warps (zero records: ncells = 0)
-      h->h_seg_recoff.assign(h->nseg, -1);
-      h->h_seg_lanes.assign(h->nseg, 0);
-      std::vector<int64_t> seginfo(4 * (size_t)std::max(h->nseg, 1), 0);
+      std::vector<int64_t> seginfo;
       int64_t nrec = 0;
       for (int sg = 0; sg < h->nseg; ++sg)
-      {
-        const int maxnf = h->h_colour_maxnf[sg], nfast = h->h_colour_fast[sg];
-        const int lanes = (nfast == 0 || maxnf > 16) ? 0 : (maxnf <= 4 ? 4 : (maxnf <= 8 ? 8 : 16));
-        seginfo[4 * sg] = h->h_colour_off[sg];
-        seginfo[4 * sg + 1] = nfast;
-        seginfo[4 * sg + 2] = lanes;
-        seginfo[4 * sg + 3] = nrec;
-        if (lanes)
+        for (auto& sub : h->h_seg_subs[sg])
         {
-          h->h_seg_recoff[sg] = nrec;
-          h->h_seg_lanes[sg] = lanes;
-          nrec += ((int64_t)nfast * lanes + 127) / 128 * 128;
+          sub.recoff = nrec;
+          seginfo.insert(seginfo.end(), {(int64_t)sub.first, (int64_t)sub.count, (int64_t)sub.lanes, nrec});
+          nrec += ((int64_t)sub.count * sub.lanes + 127) / 128 * 128;
         }
-      }
+      h->nsub = (int)(seginfo.size() / 4);
+      if (seginfo.empty())
+        seginfo.assign(4, 0);
       h->d_prec.alloc((size_t)std::max<int64_t>(nrec, 128));
       h->d_prec.zero(h->stream);
       h->d_seginfo.upload(seginfo.data(), seginfo.size());
@@ -1061,6 +1081,35 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
   // (grouped boundary patches of the stress path read the accumulated global stress: not staged)
   const bool pipelined = h->nchunk > 1 && !h->interface_first && !(h->flags & EQLB_FLAG_ATOMIC) && h->h_group_off.empty()
                          && !korn && h->nseg == h->nchunk * h->ncolours;
+  // large caller buffers in pageable memory (first call on a new mesh, nobody registered them): worker threads
+  // stage them through the pinned pool (staged_copy.cu) - 3-5x the speed of cudaMemcpy from pageable memory and
+  // no registration cost; the stage pipeline below needs page-locked buffers (eqlb_pin_host)
+  auto big_pageable = [](const void* p, size_t bytes) { return bytes >= (size_t(8) << 20) && !host_is_pinned(p); };
+  bool pageable = false;
+  for (int r = 0; r < nrhs; ++r)
+    pageable = pageable || big_pageable(G[r], nG * 8) || big_pageable(f[r], nF * 8) || (!sigma_dev && big_pageable(sigma[r], nS * 8));
+  if (pageable)
+  {
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));  // the copies run on the pool's streams
+    for (int r = 0; r < nrhs; ++r)
+    {
+      eqlb_h2d((void*)dG[r], G[r], nG * 8);
+      eqlb_h2d((void*)dF[r], f[r], nF * 8);
+      if (zeroed)
+        CUDA_CHECK(cudaMemsetAsync(dS[r], 0, nS * 8, h->stream));
+      else if (!sigma_dev)
+        eqlb_h2d(dS[r], sigma[r], nS * 8);
+    }
+    if (korn)
+      CUDA_CHECK(cudaMemcpyAsync(dK, korn, (size_t)h->ncell * 8, cudaMemcpyHostToDevice, h->stream));
+    launch();
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < nrhs && !sigma_dev; ++r)
+      eqlb_d2h(sigma[r], dS[r], nS * 8);
+    if (korn)
+      CUDA_CHECK(cudaMemcpy(korn, dK, (size_t)h->ncell * 8, cudaMemcpyDeviceToHost));
+    return;
+  }
   if (!pipelined)
   {
     for (int r = 0; r < nrhs; ++r)

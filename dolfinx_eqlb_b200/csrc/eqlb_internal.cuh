@@ -10,7 +10,8 @@
 
 #include "../../include/eqlb_b200.h"
 
-#define EQLB_NCMAX 16  // hard upper bound of cells per patch supported by the kernels
+#define EQLB_NCMAX 32      // hard upper bound of cells per patch supported by the kernels
+#define EQLB_KMAX_WIDE 3   // ... patches with 17..32 cells: flux degrees <= 3 only (generic kernel frame size)
 #define EQLB_MAXRHS 8  // max number of simultaneously equilibrated fluxes
 
 // Reciprocal for the pivots / determinants of the patch kernels: hardware approximation
@@ -60,6 +61,11 @@ void eqlb_set_error(const std::string& msg);
 // ---------------------------------------------------------------------------
 // simple owning device buffer
 // ---------------------------------------------------------------------------
+// pageable host <-> device through the pinned staging pool (staged_copy.cu); blocking
+bool host_is_pinned(const void* p);
+void eqlb_h2d(void* dst_dev, const void* src_host, size_t bytes);
+void eqlb_d2h(void* dst_host, const void* src_dev, size_t bytes);
+
 template <typename T>
 struct DevBuf
 {
@@ -90,7 +96,7 @@ struct DevBuf
   {
     alloc(count);
     if (count)
-      CUDA_CHECK(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+      eqlb_h2d(p, host, count * sizeof(T));
   }
   void zero(cudaStream_t s = 0)
   {
@@ -217,7 +223,6 @@ struct eqlb_handle
   // patches
   std::vector<int32_t> h_order;       // colour-sorted node order
   std::vector<int32_t> h_colour_off;  // [ncolours+1]
-  std::vector<int32_t> h_colour_maxnf; // [ncolours] max number of patch facets among those
   std::vector<int32_t> h_colour_fast; // [ncolours] number of leading patches of the colour eligible for the k=2 kernel
   DevBuf<double> d_k1tab;             // gathered tables of the degree-1 kernel
   DevBuf<double> d_k2tab;             // gathered tables of the k=2 streaming kernel
@@ -231,9 +236,16 @@ struct eqlb_handle
   DevBuf<uint8_t> d_pncells, d_prhs;
   DevBuf<uint16_t> d_pinfo;
   DevBuf<int4> d_prec;                  // lane records of the eligible head of every segment
-  std::vector<int64_t> h_seg_recoff;    // [nseg] offset of the segment in d_prec (-1: none)
-  std::vector<int32_t> h_seg_lanes;     // [nseg] lanes per patch (4, 8, 16; 0: none)
-  DevBuf<int64_t> d_seginfo;            // [nseg][4] first, nfast, lanes, recoff
+  // the eligible head of a segment is ordered by lane class (patches with <= 4 / 8 / 16 facets) and launched
+  // class by class, so that one high-degree vertex does not widen the lanes of a whole colour
+  struct FastSub
+  {
+    int32_t first, count, lanes;  // range in h_order, lanes per patch (4, 8, 16)
+    int64_t recoff;               // offset of its lane records in d_prec
+  };
+  std::vector<std::vector<FastSub>> h_seg_subs;  // [nseg] (empty: no lane-per-cell launch)
+  int nsub = 0;
+  DevBuf<int64_t> d_seginfo;            // [nsub][4] first, count, lanes, recoff
 
   // host pipeline (EQLB_FLAG_HOST_PIPELINE): spatial stages = chunks of the cell range
   int nchunk = 1;

@@ -768,7 +768,7 @@ void launch_patch_builder(eqlb_handle* h, int32_t* x_ncells, int32_t* x_cells, i
   patch_builder_kernel<<<(h->nactive + bs - 1) / bs, bs, 0, h->stream>>>(
       h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nactive, h->pstride, h->ncmax,
       expand ? nullptr : h->d_pnode.p, h->d_pncells.p, expand ? nullptr : h->d_pcell.p, h->d_pinfo.p,
-      expand ? nullptr : h->d_prhs.p, expand ? nullptr : h->d_prec.p, h->d_seginfo.p, h->nseg, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
+      expand ? nullptr : h->d_prhs.p, expand ? nullptr : h->d_prec.p, h->d_seginfo.p, h->nsub, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->launches++;

@@ -1605,11 +1605,16 @@ static void launch_k2_range(eqlb_handle* h, const RhsPtrs& ptrs, int first, int 
       // SE with the weak-symmetry stage fused in (interior patches)
       if constexpr (!EV)
       {
-        constexpr int minb = 3;
+        // resident CTAs per SM: 3 (168 registers, no spills) or 4 (128 registers, 20..120 spilled doubles);
+        // EQLB_K2S_MINB selects, measurements in profiles/r2_kernel_experiments.md
+        static const int minb_env = getenv("EQLB_K2S_MINB") ? atoi(getenv("EQLB_K2S_MINB")) : 3;
+        const int minb = (minb_env == 4) ? 4 : 3;
         const int tile = (S == 4) ? K2Stress<4>::TILE : (S == 8 ? K2Stress<8>::TILE : K2Stress<16>::TILE);
         const size_t smem_s = ((size_t)K2_TAB_STRESS + (size_t)(bs / S) * tile) * sizeof(double);
-        auto kern = (S == 4) ? patch_k2w_kernel<false, 4, minb, true>
-                             : (S == 8 ? patch_k2w_kernel<false, 8, minb, true> : patch_k2w_kernel<false, 16, minb, true>);
+        auto kern = (minb == 3) ? ((S == 4) ? patch_k2w_kernel<false, 4, 3, true>
+                                            : (S == 8 ? patch_k2w_kernel<false, 8, 3, true> : patch_k2w_kernel<false, 16, 3, true>))
+                                : ((S == 4) ? patch_k2w_kernel<false, 4, 4, true>
+                                            : (S == 8 ? patch_k2w_kernel<false, 8, 4, true> : patch_k2w_kernel<false, 16, 4, true>));
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * minb));
         kern<<<grid, bs, smem_s, h->stream>>>(pv, first, count, h->d_k2tab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p, bstride,

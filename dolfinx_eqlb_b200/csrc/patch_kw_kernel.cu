@@ -13,6 +13,8 @@
 // se/solve_patch_semiexplt.hpp:212-1163 (SE) and the null-space form of
 // ev/solve_patch.hpp:58-239 (EV); patches that may need `reversion_required` and the
 // stress path stay on the generic kernel.
+#include <type_traits>
+
 #include "eqlb_internal.cuh"
 
 namespace
@@ -94,8 +96,10 @@ __device__ __forceinline__ void inv_spd(const double (&A)[N][N], double (&Ai)[N]
   }
 }
 
-template <int K, bool EV, int S>
-__global__ void __launch_bounds__(128, (K == 2 ? 4 : 2))
+// MINB: resident CTAs per SM the register allocation is held to (degree 3: 2 -> 254 registers, 3 -> 168 with
+// ~10 spilled doubles, 4 -> 128; EQLB_KW3_MINB selects, measurements in profiles/r2_kernel_experiments.md)
+template <int K, bool EV, int S, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 patch_kw_kernel(PatchView pv, int first, int count, const double* __restrict__ tab, const double* __restrict__ cellJ, int nrhs,
                 RhsPtrs ptrs, const double* __restrict__ bflux, size_t bflux_stride, int use_atomics,
                 const int4* __restrict__ rec, int nfct, int nwt)
@@ -1024,6 +1028,10 @@ void build_kw_tables_t(eqlb_handle* h, const eqlb_tables* t, DevBuf<double>& dst
   dst.upload(tab.data(), tab.size());
 }
 
+#ifndef EQLB_KW3_MINB_DEFAULT
+#define EQLB_KW3_MINB_DEFAULT 2
+#endif
+
 template <int K, bool EV>
 void launch_kw_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int use_atomics, int S, int64_t recoff)
 {
@@ -1035,8 +1043,22 @@ void launch_kw_t(eqlb_handle* h, const RhsPtrs& ptrs, int first, int count, int 
   const int nwt = (count + (32 / S) - 1) / (32 / S);  // warp tiles
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-  const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * (K == 2 ? 4 : 2)));
-  auto kern = (S == 4) ? patch_kw_kernel<K, EV, 4> : (S == 8 ? patch_kw_kernel<K, EV, 8> : patch_kw_kernel<K, EV, 16>);
+  static const int minb3 = getenv("EQLB_KW3_MINB") ? atoi(getenv("EQLB_KW3_MINB")) : EQLB_KW3_MINB_DEFAULT;
+  const int minb = (K == 2) ? 4 : std::min(4, std::max(2, minb3));
+  const int grid = std::max(1, std::min((nwt + 3) / 4, nsm * minb));
+  using kern_t = void (*)(PatchView, int, int, const double*, const double*, int, RhsPtrs, const double*, size_t, int, const int4*,
+                          int, int);
+  kern_t kern = nullptr;
+  auto pick = [&](auto mb)
+  {
+    constexpr int MB = decltype(mb)::value;
+    return (S == 4) ? patch_kw_kernel<K, EV, 4, MB> : (S == 8 ? patch_kw_kernel<K, EV, 8, MB> : patch_kw_kernel<K, EV, 16, MB>);
+  };
+  if constexpr (K == 2)
+    kern = pick(std::integral_constant<int, 4>{});
+  else
+    kern = (minb == 2) ? pick(std::integral_constant<int, 2>{})
+                       : (minb == 3 ? pick(std::integral_constant<int, 3>{}) : pick(std::integral_constant<int, 4>{}));
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, bs, smem, h->stream>>>(h->patch_view(), first, count, h->d_kwtab.p, h->d_cellJ.p, h->nrhs, ptrs, h->d_bflux.p,
                                       (size_t)h->ncell * h->nrt, use_atomics, h->d_prec.p + recoff, h->nfct, nwt);

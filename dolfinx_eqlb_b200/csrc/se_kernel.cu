@@ -1241,6 +1241,24 @@ patch_kernel(PatchView pv, int first, int count, TableView tv, const double* __r
   }
 }
 
+// Instantiations by the largest patch of the mesh: 8 / 16 cells, and 32 cells for degrees <= 3 (the
+// per-thread frame of the dense patch system grows with NCMAX^2: 18 KB at k=2, 107 KB at k=3; degree 4
+// would need 340 KB per thread and stays at 16).
+using patch_kernel_t = void (*)(PatchView, int, int, TableView, const double*, const int32_t*, int, RhsPtrs, const double*, size_t,
+                                int, const int32_t*, int, int);
+template <int K, int NDG, bool EV, bool STRESS>
+patch_kernel_t select_kernel(int ncmax)
+{
+  if (ncmax <= 8)
+    return patch_kernel<K, NDG, 8, EV, STRESS>;
+  if (ncmax <= 16)
+    return patch_kernel<K, NDG, 16, EV, STRESS>;
+  if constexpr (K <= EQLB_KMAX_WIDE)
+    return patch_kernel<K, NDG, EQLB_NCMAX, EV, STRESS>;
+  throw EqlbError(EQLB_ERR_INPUT, "eqlb_b200: patches with more than 16 cells are supported up to flux degree "
+                                      + std::to_string(EQLB_KMAX_WIDE) + " (largest patch: " + std::to_string(ncmax) + " cells)");
+}
+
 template <int K, int NDG, bool EV>
 void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
 {
@@ -1257,11 +1275,11 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   const bool atomics = (h->flags & EQLB_FLAG_ATOMIC) != 0;
   const bool stress = !EV && (h->flags & EQLB_FLAG_STRESS) != 0 && K >= 2;
   constexpr bool CAN_STRESS = !EV && K >= 2 && K <= 4;
-  auto kern = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, false> : patch_kernel<K, NDG, EQLB_NCMAX, EV, false>;
+  auto kern = select_kernel<K, NDG, EV, false>(h->ncmax);
   if (stress)
   {
     if constexpr (CAN_STRESS)
-      kern = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, true> : patch_kernel<K, NDG, EQLB_NCMAX, EV, true>;
+      kern = select_kernel<K, NDG, EV, true>(h->ncmax);
     else
       throw EqlbError(EQLB_ERR_INPUT, "stress equilibration: flux degree not supported by the CUDA kernel");
   }
@@ -1278,7 +1296,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       for (size_t g = 0; g + 1 < h->h_group_off.size(); ++g)
       {
         const int first = h->h_group_off[g], count = h->h_group_off[g + 1] - first;
-        auto kplain = (h->ncmax <= 8) ? patch_kernel<K, NDG, 8, EV, false> : patch_kernel<K, NDG, EQLB_NCMAX, EV, false>;
+        auto kplain = select_kernel<K, NDG, EV, false>(h->ncmax);
         CUDA_CHECK(cudaFuncSetAttribute(kplain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kplain<<<1, bs, smem, h->stream>>>(pv, first, count, h->tv, h->d_cellJ.p, dgmap, h->nrhs, ptrs, h->d_bflux.p, bstride,
                                            1, h->d_cell_fct.p, h->nfct, 0);
@@ -1310,29 +1328,31 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       static const bool stress_fast = getenv("EQLB_STRESS_GENERIC") == nullptr;
       const bool k2ok = (K == 2 && NDG == 3 && h->d_k2tab.p);
       const bool k1ok = (K == 1 && NDG == 1 && h->d_k1tab.p);
-      if (!(h->flags & EQLB_FLAG_GENERIC) && h->h_colour_maxnf[c] <= 16 && h->h_seg_lanes[c] > 0
+      if (!(h->flags & EQLB_FLAG_GENERIC) && !h->h_seg_subs[c].empty()
           && (stress ? (k2ok && stress_fast && !EV) : (k1ok || k2ok || (kw_supported(K, NDG) && h->d_kwtab.p))))
       {
-        // specialised kernels for the eligible head of the segment, generic kernel for the rest
+        // specialised kernels for the eligible head of the segment (one launch per lane class), generic
+        // kernel for the rest
         static const bool force_kw = getenv("EQLB_KW") != nullptr;
         // Within one colour every DOF is touched by exactly one patch, so the accumulation can
         // use fire-and-forget RED.ADD.F64 and stay bitwise deterministic (the colours are
         // serialised on the stream); measured 14-25 % faster than load-add-store.
         static const int use_red = getenv("EQLB_RED") ? atoi(getenv("EQLB_RED")) : 1;
-        const int nfast = h->h_colour_fast[c];
         // programmatic dependent launch behind a kernel of this very call (never behind foreign work
         // that may still be producing G or f)
         static const bool pdl_on = getenv("EQLB_PDL") ? atoi(getenv("EQLB_PDL")) != 0 : true;
-        if (K == 1)
-          launch_k1(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c], pdl_on && launched_before && use_red);
-        else if (K == 2 && (!force_kw || stress))
+        for (const auto& sub : h->h_seg_subs[c])
         {
-          launch_k2(h, EV, ptrs, first, nfast, use_red, h->h_colour_maxnf[c], h->h_seg_lanes[c], h->h_seg_recoff[c], stress,
-                    pdl_on && launched_before && use_red);
+          const bool pdl = pdl_on && launched_before && use_red;
+          if (K == 1)
+            launch_k1(h, EV, ptrs, sub.first, sub.count, use_red, sub.lanes, sub.recoff, pdl);
+          else if (K == 2 && (!force_kw || stress))
+            launch_k2(h, EV, ptrs, sub.first, sub.count, use_red, sub.lanes, sub.lanes, sub.recoff, stress, pdl);
+          else
+            launch_kw(h, EV, ptrs, sub.first, sub.count, use_red, sub.lanes, sub.recoff);
+          launched_before = true;
         }
-        else
-          launch_kw(h, EV, ptrs, first, nfast, use_red, h->h_seg_lanes[c], h->h_seg_recoff[c]);
-        launched_before = launched_before || nfast > 0;
+        const int nfast = h->h_colour_fast[c];
         first += nfast;
         count -= nfast;
       }
@@ -1347,57 +1367,71 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
   }
 }
 
+// This file is compiled in EQLB_SE_PARTS translation units (-DEQLB_SE_PART=n, see the Makefile): each part
+// instantiates the kernels of some (degree_flux, degree_dg) combinations, so that the parts build in parallel.
+#ifndef EQLB_SE_PART
+#error "se_kernel.cu: compile with -DEQLB_SE_PART=1..4"
+#endif
+#define SE_CASE(part, KK, ND)                                                                                          \
+  case KK * 100 + ND:                                                                                                  \
+    if constexpr (EQLB_SE_PART == part)                                                                                \
+    {                                                                                                                  \
+      launch_patch_t<KK, ND, EV>(h, dG, dF, dSigma);                                                                   \
+      return true;                                                                                                     \
+    }                                                                                                                  \
+    return false;
+
 template <bool EV>
-void dispatch(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
+bool dispatch(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
 {
-  const int key = h->k * 100 + h->ndg;
-  switch (key)
+  switch (h->k * 100 + h->ndg)
   {
-  case 101:
-    launch_patch_t<1, 1, EV>(h, dG, dF, dSigma);
-    break;
-  case 201:
-    launch_patch_t<2, 1, EV>(h, dG, dF, dSigma);
-    break;
-  case 203:
-    launch_patch_t<2, 3, EV>(h, dG, dF, dSigma);
-    break;
-  case 301:
-    launch_patch_t<3, 1, EV>(h, dG, dF, dSigma);
-    break;
-  case 303:
-    launch_patch_t<3, 3, EV>(h, dG, dF, dSigma);
-    break;
-  case 306:
-    launch_patch_t<3, 6, EV>(h, dG, dF, dSigma);
-    break;
-  case 401:
-    launch_patch_t<4, 1, EV>(h, dG, dF, dSigma);
-    break;
-  case 403:
-    launch_patch_t<4, 3, EV>(h, dG, dF, dSigma);
-    break;
-  case 406:
-    launch_patch_t<4, 6, EV>(h, dG, dF, dSigma);
-    break;
-  case 410:
-    launch_patch_t<4, 10, EV>(h, dG, dF, dSigma);
-    break;
+    SE_CASE(1, 1, 1)
+    SE_CASE(1, 2, 1)
+    SE_CASE(1, 2, 3)
+    SE_CASE(2, 3, 1)
+    SE_CASE(2, 3, 3)
+    SE_CASE(2, 3, 6)
+    SE_CASE(3, 4, 1)
+    SE_CASE(3, 4, 3)
+    SE_CASE(4, 4, 6)
+    SE_CASE(4, 4, 10)
   default:
-    throw EqlbError(EQLB_ERR_INPUT, "patch kernel: unsupported (degree_flux, degree_dg) combination");
+    return false;
   }
 }
 
 } // namespace
 
+#define SE_CAT2(a, b) a##b
+#define SE_CAT(a, b) SE_CAT2(a, b)
+bool SE_CAT(launch_generic_part, EQLB_SE_PART)(eqlb_handle* h, bool ev, const double* const* dG, const double* const* dF,
+                                                double* const* dSigma)
+{
+  return ev ? dispatch<true>(h, dG, dF, dSigma) : dispatch<false>(h, dG, dF, dSigma);
+}
+
+#if EQLB_SE_PART == 1
+bool launch_generic_part2(eqlb_handle*, bool, const double* const*, const double* const*, double* const*);
+bool launch_generic_part3(eqlb_handle*, bool, const double* const*, const double* const*, double* const*);
+bool launch_generic_part4(eqlb_handle*, bool, const double* const*, const double* const*, double* const*);
+
+static void launch_any(eqlb_handle* h, bool ev, const double* const* dG, const double* const* dF, double* const* dSigma)
+{
+  if (!(launch_generic_part1(h, ev, dG, dF, dSigma) || launch_generic_part2(h, ev, dG, dF, dSigma)
+        || launch_generic_part3(h, ev, dG, dF, dSigma) || launch_generic_part4(h, ev, dG, dF, dSigma)))
+    throw EqlbError(EQLB_ERR_INPUT, "patch kernel: unsupported (degree_flux, degree_dg) combination");
+}
+
 void launch_se(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma, double* dKorn)
 {
-  dispatch<false>(h, dG, dF, dSigma);
+  launch_any(h, false, dG, dF, dSigma);
   if (dKorn)
     launch_korn(h, dKorn);
 }
 
 void launch_ev(eqlb_handle* h, const double* const* dG, const double* const* dF, double* const* dSigma)
 {
-  dispatch<true>(h, dG, dF, dSigma);
+  launch_any(h, true, dG, dF, dSigma);
 }
+#endif

@@ -386,6 +386,7 @@ class FluxEquilibrator:
         self.list_bfunctions = []
         self.boundary_data = None
         self._pinned = []
+        self._pin_pending = None  # host vectors to page-lock before the second call (see _note_call)
 
     def _pin(self, arrays, min_bytes=4 << 20):
         """Page-lock large host vectors once (`eqlb_pin_host`) so that the host-pointer calls copy
@@ -395,6 +396,17 @@ class FluxEquilibrator:
             if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.nbytes >= min_bytes:
                 if lib.eqlb_pin_host(a.ctypes.data, a.nbytes) == 0:
                     self._pinned.append(a)
+
+    def _note_call(self):
+        """The first call on a new problem runs from pageable memory (the library stages the copies through its
+        pinned pool); registering the caller's vectors costs about one such call and is done when a second call
+        shows that the problem is reused (time loops) - then the stage pipeline takes over."""
+        if self._pin_pending is not None:
+            if self._pin_pending[0] >= 1:
+                self._pin(self._pin_pending[1])
+                self._pin_pending = None
+            else:
+                self._pin_pending[0] += 1
 
     def __del__(self):
         try:
@@ -425,7 +437,7 @@ class FluxEqlbSE(FluxEquilibrator):
         self.list_flux = [np.zeros(msh.ncell * self.tables.nrt) for _ in range(self.n_fluxes)]
         self._fresh = True  # list_flux still holds the zeros it was created with
         if host_pipeline:
-            self._pin(self.list_flux + list(list_rhs) + list(list_proj_flux))
+            self._pin_pending = [0, self.list_flux + list(list_rhs) + list(list_proj_flux)]
 
     def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux, device=False):
         """`device=True`: the boundary data are built on the GPU (`eqlb_set_bcs_poly`); else by the host mirror
@@ -442,6 +454,7 @@ class FluxEqlbSE(FluxEquilibrator):
         self.problem.set_bcs(self.boundary_data)
 
     def equilibrate_fluxes(self):
+        self._note_call()
         reconstruct_fluxes_semiexplt(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, self.korn_constants,
                                      zeroed=self._fresh)
         self._fresh = False
@@ -480,7 +493,7 @@ class FluxEqlbEV(FluxEquilibrator):
         self.list_flux = [np.zeros(self.ndofs) for _ in range(self.n_fluxes)]
         self._fresh = True
         if host_pipeline:
-            self._pin(self.list_flux + list(list_rhs) + list(list_proj_flux))
+            self._pin_pending = [0, self.list_flux + list(list_rhs) + list(list_proj_flux)]
 
     def set_boundary_conditions(self, list_bfct_prime, list_bcs_flux, device=False):
         if self.n_fluxes != len(list_bfct_prime) or self.n_fluxes != len(list_bcs_flux):
@@ -495,6 +508,7 @@ class FluxEqlbEV(FluxEquilibrator):
         self.problem.set_bcs(self.boundary_data)
 
     def equilibrate_fluxes(self):
+        self._note_call()
         reconstruct_fluxes_minimisation(self.problem, self.list_flux, self.list_proj_flux, self.list_rhs, zeroed=self._fresh)
         self._fresh = False
 

@@ -256,6 +256,57 @@ def random_diagonal_square(n: int, seed: int = 3, scramble_seed: int | None = No
     return build_topology(x, tris)
 
 
+def fan_unit_square(nper: int, hub_on_boundary: bool = False, scramble_seed: int | None = None) -> Mesh:
+    """Unit square triangulated as ONE fan: every cell joins the hub vertex with two neighbouring points of
+    the perimeter (`nper` segments per side).  Hub in the interior: an interior patch with 4 nper cells; hub
+    at the middle of the bottom side: a boundary patch with 3 nper cells.  All other patches have 2..4 cells.
+    Stand-in for the high-valence vertices of unstructured meshes (patches with more than 16 cells)."""
+    t = np.arange(nper) / nper
+    one, zero = np.ones(nper), np.zeros(nper)
+    sides = [np.stack([t, zero], 1), np.stack([one, t], 1), np.stack([1.0 - t, one], 1), np.stack([zero, 1.0 - t], 1)]
+    if hub_on_boundary:
+        ring = np.concatenate([np.array([[1.0, 0.0]]), sides[1][1:], sides[2], sides[3], np.array([[0.0, 0.0]])])
+        hub = np.array([[0.5, 0.0]])
+        nr = ring.shape[0]
+        # the two corner points next to the hub would sit in one cell only (the reference rejects 1-cell
+        # patches, se/Patch.cpp:353-359): split the first and last pair of fan cells through the midpoints
+        # of the edges hub-ring[1] and hub-ring[nr-2]
+        mids = 0.5 * (hub + ring[[1, nr - 2]])
+        x = np.concatenate([ring, hub, mids])
+        h, ma, mb = nr, nr + 1, nr + 2
+        tris = [[h, i, i + 1] for i in range(2, nr - 3)]
+        tris += [[h, 0, ma], [0, 1, ma], [h, ma, 2], [ma, 1, 2]]
+        tris += [[h, mb, nr - 1], [mb, nr - 2, nr - 1], [h, nr - 3, mb], [nr - 3, nr - 2, mb]]
+        tris = np.array(tris)
+    else:
+        ring = np.concatenate(sides)
+        hub = np.array([[0.5, 0.5]])
+        x = np.concatenate([ring, hub])
+        nr = ring.shape[0]
+        tris = np.stack([np.full(nr, nr), np.arange(nr), (np.arange(nr) + 1) % nr], axis=1)
+    tris = np.sort(tris, axis=1)
+    if scramble_seed is not None:
+        tris = _scramble(tris, np.random.default_rng(scramble_seed))
+    return build_topology(x, tris.astype(np.int32))
+
+
+def submesh(mesh: Mesh, cells: np.ndarray):
+    """Sub-mesh of the given cells with an ORDER-PRESERVING renumbering of vertices (and hence of facets and of
+    the adjacency lists): a vertex whose whole patch lies in the sub-mesh sees exactly the patch it has in
+    `mesh` (same start facet, same cell order, same facet orientations).  Returns (sub, nodes, facets): the
+    vertex / facet ids of `mesh` for every vertex / facet of `sub`.  Used to replay windows of a full-size
+    problem on the CPU oracle (tests/test_gpu_fullsize.py)."""
+    cells = np.sort(np.asarray(cells, dtype=np.int64))
+    cn = mesh.cell_node[cells]
+    nodes = np.unique(cn)
+    sub = build_topology(mesh.x[nodes], np.searchsorted(nodes, cn).astype(np.int32))
+    pairs = nodes[sub.fct_node]
+    key_full = mesh.fct_node[:, 0].astype(np.int64) * mesh.nnode + mesh.fct_node[:, 1]
+    facets = np.searchsorted(key_full, pairs[:, 0].astype(np.int64) * mesh.nnode + pairs[:, 1])
+    assert np.array_equal(mesh.fct_node[facets], pairs)
+    return sub, nodes.astype(np.int64), facets.astype(np.int64)
+
+
 def pk_dofmap(mesh: Mesh, q: int):
     """Cell dofmap [ncell][(q+1)(q+2)/2] of the continuous P_q space (q <= 3) in Basix' cell-local DOF order
     (vertices, edge interiors e0 e1 e2 from the lower to the higher global vertex, cell interior), numbered

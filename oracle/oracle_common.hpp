@@ -1,13 +1,14 @@
 // TEST INFRASTRUCTURE - NOT PRODUCT CODE.
 // CPU restatement ("oracle") of the dolfinx_eqlb hot path. Only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
-// may load this.  PARITY PINNING: the reference has no golden vectors and
-// cannot be built here (needs DOLFINx/Basix/Eigen); the oracle is
-// pinned by the reference's own acceptance invariants (tests/test_oracle_*.py):
-// divergence, H(div) jump, flux-BC and weak-symmetry conditions, and EV == SE.
-// Against OUTPUTS of the reference itself the oracle is "parity unpinned": no DOLFINx run is
-// possible in the build image; tools/export_dolfinx_fixture.py + tests/test_dolfinx_fixtures.py
-// close that gap as soon as a fixture from a live installation is added.
+// may load this.  PARITY PINNING: PINNED against the reference's own code.  oracle/_ref/libeqlb_ref.so
+// is the reference's C++ (se/, ev/, base/ sources and header templates) compiled UNCHANGED against the
+// stand-in headers of oracle/ref_shim (oracle/Makefile target `ref`); tests/test_ref_pinning.py and
+// tests/test_ref_bcs.py compare this restatement with it (integer maps bit-exact, DOF vectors <= 1e-11),
+// the goldens under tests/golden/ are its outputs, and the RT element tables are checked against the
+// reference's e_raviart_thomas.py executed on a stand-in basix module (tests/golden/ref_rt_element.npz).
+// Restated rather than compiled (third party, absent): Basix quadrature points / Lagrange variants, FFCx
+// form kernels, DOLFINx DOF transformations, Eigen - see DESIGN.md section 6 for what that leaves open.
 #pragma once
 
 #include <algorithm>

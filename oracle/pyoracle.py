@@ -3,8 +3,8 @@
 ctypes loader of the CPU oracle (`oracle/liboracle.so`, built by
 `oracle/Makefile`).  Only tests/, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of bench.py may import this module.
-Pinned by the reference's acceptance invariants and the golden vectors generated under them;
-against outputs of the reference itself: parity unpinned (see oracle_common.hpp).
+Parity pinned: checked against the reference's own sources compiled unchanged (`oracle/_ref`, loaded by
+`oracle/pyref.py`) in tests/test_ref_pinning.py, and against the golden vectors generated from it.
 """
 
 from __future__ import annotations

@@ -11,6 +11,10 @@ def make_mesh(kind, n, scramble=None, perturb=0.0):
         return ms.crossed_unit_square(n, scramble_seed=scramble, perturb=perturb)
     if kind == "randdiag":
         return ms.random_diagonal_square(n, seed=11, scramble_seed=scramble, perturb=perturb)
+    if kind == "fan":  # interior hub with 4 n cells
+        return ms.fan_unit_square(n, False, scramble_seed=scramble)
+    if kind == "halffan":  # boundary hub with 3 n cells
+        return ms.fan_unit_square(n, True, scramble_seed=scramble)
     raise ValueError(kind)
 
 

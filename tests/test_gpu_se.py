@@ -179,7 +179,7 @@ def fan_mesh(nfan, seed=0):
     return ms.build_topology(x[perm], inv[np.array(tris)].astype(np.int32))
 
 
-@pytest.mark.parametrize("nfan", [9, 13, 16])
+@pytest.mark.parametrize("nfan", [9, 13, 16, 20, 32])  # > 16: generic kernel for the hub, lane kernels for the rest
 @pytest.mark.parametrize("k", [1, 2, 3])
 def test_high_valence_patches(nfan, k):
     """Patches with 9..16 cells take the S = 16 lane variants; parity against the oracle for SE, EV
@@ -214,11 +214,12 @@ def test_high_valence_patches(nfan, k):
 
 
 def test_too_many_cells_is_an_error():
-    """More than 16 cells around a vertex: rejected loudly by eqlb_create (no silent fallback)."""
+    """More than 32 cells around a vertex: rejected loudly by eqlb_create (no silent fallback); 17..32 cells
+    are served by the generic kernel (tests/test_large_patches.py)."""
     from dolfinx_eqlb_b200 import tables as tb
 
-    m = fan_mesh(17, seed=1)
+    m = fan_mesh(33, seed=1)
     T = tb.make_tables(2)
     z = [np.zeros(m.ncell * T.ndg)]
-    with pytest.raises(RuntimeError, match="more than 16 cells"):
+    with pytest.raises(RuntimeError, match="more than 32 cells"):
         eqlb.FluxEqlbSE(2, m, z, [np.zeros(m.ncell * T.ndg * 2)])

@@ -67,7 +67,7 @@ def _ptr(a, ctype):
 class PackedMesh:
     """Owns contiguous copies of the mesh arrays and the C struct view."""
 
-    def __init__(self, mesh, ndg, node_owned=None):
+    def __init__(self, mesh, ndg, node_owned=None, identity_dg_as_null=False):
         from .mesh import dg_dofmap
 
         self.mesh = mesh
@@ -85,7 +85,14 @@ class PackedMesh:
             setattr(s, name, _ptr(keep(name, getattr(mesh, name), np.int32), C.c_int32))
         s.fct_perms = _ptr(keep("fct_perms", mesh.fct_perms, np.uint8), C.c_uint8)
         s.cell_perm_info = _ptr(keep("cell_perm_info", mesh.cell_perm_info, np.uint32), C.c_uint32)
-        s.dg_dofmap = _ptr(keep("dg_dofmap", dg_dofmap(mesh.ncell, ndg), np.int32), C.c_int32)
+        # DG_p dofmap: the mirror's spaces use the DOLFINx layout cell*ndg + i.  The CUDA library assumes that layout for
+        # a NULL pointer (`identity_dg_as_null`: saves building and checking a 12 M entry array per handle; a binding
+        # passes V_dg.dofmap()->list()); the CPU oracles take the explicit map.
+        custom = getattr(mesh, "dg_dofmap", None)
+        if custom is not None:
+            s.dg_dofmap = _ptr(keep("dg_dofmap", custom, np.int32), C.c_int32)
+        elif not identity_dg_as_null:
+            s.dg_dofmap = _ptr(keep("dg_dofmap", dg_dofmap(mesh.ncell, ndg), np.int32), C.c_int32)
         if node_owned is not None:
             s.node_owned = _ptr(keep("node_owned", node_owned, np.uint8), C.c_uint8)
         self.struct = s

@@ -80,30 +80,51 @@ void colour_patches(eqlb_handle* h)
     throw EqlbError(EQLB_ERR_STATE, "colouring: host topology not available");
   }
   const int n = h->nnode;
-  h->h_colour.assign(n, -1);
   int ncol = 0;
+  const auto t_enter = std::chrono::steady_clock::now();
   const int ngrouped = h->h_group_off.empty() ? 0 : h->h_group_off.back();
-  for (int z = 0; z < n; ++z)
+  static const bool host_col = getenv("EQLB_HOST_COLOURING") && atoi(getenv("EQLB_HOST_COLOURING")) != 0;
+  if (host_col || !h->d_node_cell.p || !h->d_cell_node.p)
   {
-    if (!h->h_owned[z] || h->h_grouped[z])
-      continue;
-    uint64_t used = 0;
-    for (int i = T.node_cell_off[z]; i < T.node_cell_off[z + 1]; ++i)
+    // sequential first-fit colouring on the host (reference implementation of the device kernel)
+    h->h_colour.assign(n, -1);
+    for (int z = 0; z < n; ++z)
     {
-      const int32_t* cn = &T.cell_node[3 * (size_t)T.node_cell[i]];
-      for (int j = 0; j < 3; ++j)
+      if (!h->h_owned[z] || h->h_grouped[z])
+        continue;
+      uint64_t used = 0;
+      for (int i = T.node_cell_off[z]; i < T.node_cell_off[z + 1]; ++i)
       {
-        const int c = h->h_colour[cn[j]];
-        if (c >= 0)
-          used |= (uint64_t(1) << c);
+        const int32_t* cn = &T.cell_node[3 * (size_t)T.node_cell[i]];
+        for (int j = 0; j < 3; ++j)
+        {
+          const int c = h->h_colour[cn[j]];
+          if (c >= 0)
+            used |= (uint64_t(1) << c);
+        }
       }
+      int c = 0;
+      while (used & (uint64_t(1) << c))
+        ++c;
+      h->h_colour[z] = c;
+      ncol = std::max(ncol, c + 1);
     }
-    int c = 0;
-    while (used & (uint64_t(1) << c))
-      ++c;
-    h->h_colour[z] = c;
-    ncol = std::max(ncol, c + 1);
   }
+  else
+  {
+    // the same colouring, computed on the device from the uploaded connectivity (patch_builder.cu)
+    std::vector<uint8_t> skip(n);
+    bool any = false;
+    for (int z = 0; z < n; ++z)
+    {
+      skip[z] = (!h->h_owned[z] || h->h_grouped[z]) ? 1 : 0;
+      any = any || skip[z];
+    }
+    ncol = device_greedy_colouring(h, any ? skip.data() : nullptr, h->h_colour);
+  }
+  StageTimer ctm;
+  ctm.t0 = t_enter;
+  ctm.lap("  colouring: first-fit colours");
   h->ncolours = ncol;
   // Launch segments: (spatial chunk, colour).  One colour of the whole mesh streams all
   // inputs through HBM once per colour (ncu round 1: 3 x 0.68 GB read per step); with the
@@ -153,29 +174,48 @@ void colour_patches(eqlb_handle* h)
   };
   h->nseg = nchunk * ncol;
   h->h_colour_off.assign(h->nseg + 1, 0);
-  auto seg_of = [&](int z) { return chunk_of(z) * ncol + h->h_colour[z]; };
+  // segment and lane class of every active patch, evaluated once (several host threads).
+  // Lane class: patches eligible for the lane-per-cell kernels (interior patches, or any patch of a
+  // single-RHS problem: `reversion_required` cannot occur there; at most 16 facets) by facet count
+  // 4 / 8 / 16 -> 0 / 1 / 2, everything else 3.
+  std::vector<int32_t> vseg(n, -1);
+  std::vector<int8_t> vcls(n, 3);
+  {
+    const int nthr = n > (1 << 16) ? std::max(1, std::min(6, (int)std::thread::hardware_concurrency() / 2)) : 1;
+    auto part = [&](int t)
+    {
+      const int z0 = (int)((long)n * t / nthr), z1 = (int)((long)n * (t + 1) / nthr);
+      for (int z = z0; z < z1; ++z)
+      {
+        if (!h->h_owned[z] || h->h_grouped[z])
+          continue;
+        vseg[z] = chunk_of(z) * ncol + h->h_colour[z];
+        const int nf = T.node_fct_off[z + 1] - T.node_fct_off[z], nc = T.node_cell_off[z + 1] - T.node_cell_off[z];
+        vcls[z] = (nf > 16 || !(h->nrhs == 1 || nf == nc)) ? 3 : (nf <= 4 ? 0 : (nf <= 8 ? 1 : 2));
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthr; ++t)
+      th.emplace_back(part, t);
+    part(0);
+    for (auto& x : th)
+      x.join();
+  }
+  ctm.lap("  colouring: segment / lane class");
   for (int z = 0; z < n; ++z)
-    if (h->h_owned[z] && !h->h_grouped[z])
-      h->h_colour_off[seg_of(z) + 1]++;
+    if (vseg[z] >= 0)
+      h->h_colour_off[vseg[z] + 1]++;
   h->h_colour_off[0] = ngrouped;  // grouped patches occupy the head of h_order
   for (int c = 0; c < h->nseg; ++c)
     h->h_colour_off[c + 1] += h->h_colour_off[c];
   std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
   h->h_order.resize(h->nactive);
-  // within a segment: patches eligible for the lane-per-cell kernels first (interior patches, or any
-  // patch of a single-RHS problem: `reversion_required` cannot occur there; at most 16 facets), ordered
-  // by lane class 4 / 8 / 16; a class with few members joins the next wider one (saves a launch)
-  auto lane_class = [&](int z)
-  {
-    const int nf = T.node_fct_off[z + 1] - T.node_fct_off[z], nc = T.node_cell_off[z + 1] - T.node_cell_off[z];
-    if (nf > 16 || !(h->nrhs == 1 || nf == nc))
-      return 3;
-    return nf <= 4 ? 0 : (nf <= 8 ? 1 : 2);
-  };
+  // within a segment: lane classes 4 / 8 / 16 first, then the rest; a class with few members joins the next
+  // wider one (saves a launch)
   std::vector<int32_t> ccount(3 * (size_t)h->nseg, 0);
   for (int z = 0; z < n; ++z)
-    if (h->h_owned[z] && !h->h_grouped[z] && lane_class(z) < 3)
-      ccount[3 * seg_of(z) + lane_class(z)]++;
+    if (vseg[z] >= 0 && vcls[z] < 3)
+      ccount[3 * vseg[z] + vcls[z]]++;
   std::vector<int8_t> cmap(3 * (size_t)h->nseg);
   for (int sg = 0; sg < h->nseg; ++sg)
   {
@@ -193,24 +233,28 @@ void colour_patches(eqlb_handle* h)
   }
   h->h_colour_fast.assign(h->nseg, 0);
   h->h_seg_subs.assign(h->nseg, {});
-  for (int pass = 0; pass < 4; ++pass)
+  std::vector<int32_t> start(4 * (size_t)h->nseg);
+  for (int sg = 0; sg < h->nseg; ++sg)
   {
-    if (pass < 3)
-      for (int sg = 0; sg < h->nseg; ++sg)
-        if (ccount[3 * sg + pass] > 0)
-          h->h_seg_subs[sg].push_back({pos[sg], ccount[3 * sg + pass], 4 << pass, -1});
-    for (int z = 0; z < n; ++z)
-      if (h->h_owned[z] && !h->h_grouped[z])
-      {
-        const int lc = lane_class(z), sg = seg_of(z);
-        if ((lc < 3 ? cmap[3 * sg + lc] : 3) != pass)
-          continue;
-        h->h_order[pos[sg]++] = z;
-        if (pass < 3)
-          h->h_colour_fast[sg]++;
-      }
+    int32_t at = pos[sg];
+    for (int cl = 0; cl < 3; ++cl)
+    {
+      start[4 * sg + cl] = at;
+      if (ccount[3 * sg + cl] > 0)
+        h->h_seg_subs[sg].push_back({at, ccount[3 * sg + cl], 4 << cl, -1});
+      at += ccount[3 * sg + cl];
+      h->h_colour_fast[sg] += ccount[3 * sg + cl];
+    }
+    start[4 * sg + 3] = at;
   }
+  for (int z = 0; z < n; ++z)  // vertex order within every class: the order is deterministic
+    if (vseg[z] >= 0)
+    {
+      const int lc = vcls[z], sg = vseg[z];
+      h->h_order[start[4 * sg + (lc < 3 ? cmap[3 * sg + lc] : 3)]++] = z;
+    }
 
+  ctm.lap("  colouring: launch order");
   // result ranges of the host pipeline: a range of DOFs can go back to the host after the
   // last stage with a patch that adds into it
   h->h_se_slabs.clear();
@@ -220,26 +264,48 @@ void colour_patches(eqlb_handle* h)
     std::vector<int> nstage(n, -1);
     for (int z = 0; z < n; ++z)
       if (h->h_owned[z] && !h->h_grouped[z])
-        nstage[z] = chunk_of(z);
+        nstage[z] = vseg[z] / ncol;
     auto slab_lo = [&](long cnt, int sidx) { return (size_t)(cnt * sidx / nchunk); };
     const int kk = h->k;
     const size_t ncd = (size_t)(kk * kk - kk);
+    // last stage that adds into the cells / facets of a slab (host threads: one slab each)
+    std::vector<int> cfin(nchunk, 0), ffin(nchunk, 0);
+    {
+      const int nthr = n > (1 << 16) ? std::max(1, std::min(6, (int)std::thread::hardware_concurrency() / 2)) : 1;
+      auto part = [&](int t)
+      {
+        for (int sidx = t; sidx < nchunk; sidx += nthr)
+        {
+          const size_t c0 = slab_lo(h->ncell, sidx), c1 = slab_lo(h->ncell, sidx + 1);
+          int fin = 0;
+          for (size_t c = c0; c < c1; ++c)
+            for (int j = 0; j < 3; ++j)
+              fin = std::max(fin, nstage[T.cell_node[3 * c + j]]);
+          cfin[sidx] = fin;
+          const size_t f0 = slab_lo(h->nfct, sidx), f1 = slab_lo(h->nfct, sidx + 1);
+          int ff = 0;
+          for (size_t f = f0; f < f1; ++f)
+            ff = std::max(ff, std::max(nstage[T.fct_node[2 * f]], nstage[T.fct_node[2 * f + 1]]));
+          ffin[sidx] = ff;
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nthr; ++t)
+        th.emplace_back(part, t);
+      part(0);
+      for (auto& x : th)
+        x.join();
+    }
     for (int sidx = 0; sidx < nchunk; ++sidx)
     {
       const size_t c0 = slab_lo(h->ncell, sidx), c1 = slab_lo(h->ncell, sidx + 1);
-      int fin = 0;
-      for (size_t c = c0; c < c1; ++c)
-        for (int j = 0; j < 3; ++j)
-          fin = std::max(fin, nstage[T.cell_node[3 * c + j]]);
-      h->h_se_slabs.push_back({c0 * h->nrt, (c1 - c0) * h->nrt, fin});
+      h->h_se_slabs.push_back({c0 * h->nrt, (c1 - c0) * h->nrt, cfin[sidx]});
       if (ncd)
-        h->h_ev_slabs.push_back({(size_t)h->nfct * kk + c0 * ncd, (c1 - c0) * ncd, fin});
+        h->h_ev_slabs.push_back({(size_t)h->nfct * kk + c0 * ncd, (c1 - c0) * ncd, cfin[sidx]});
       const size_t f0 = slab_lo(h->nfct, sidx), f1 = slab_lo(h->nfct, sidx + 1);
-      int ffin = 0;
-      for (size_t f = f0; f < f1; ++f)
-        ffin = std::max(ffin, std::max(nstage[T.fct_node[2 * f]], nstage[T.fct_node[2 * f + 1]]));
-      h->h_ev_slabs.push_back({f0 * kk, (f1 - f0) * kk, ffin});
+      h->h_ev_slabs.push_back({f0 * kk, (f1 - f0) * kk, ffin[sidx]});
     }
+    ctm.lap("  colouring: result slabs");
   }
 }
 
@@ -451,20 +517,8 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         // (boundary-patch grouping, recolouring).  Measured at 1024^2: upload 64-180 ms, colouring 55 ms, copies 72 ms.
         h->h_grouped.assign(nn, 0);
         h->topo = {mesh->node_cell_off, mesh->node_cell, mesh->cell_node, mesh->node_fct_off, mesh->node_fct, mesh->fct_node};
-        std::exception_ptr colour_err, copy_err;
+        std::exception_ptr copy_err, dgmap_err;
         eqlb_handle* hp = h.get();
-        std::thread colour_thread(
-            [hp, &colour_err]
-            {
-              try
-              {
-                colour_patches(hp);
-              }
-              catch (...)
-              {
-                colour_err = std::current_exception();
-              }
-            });
         std::thread copy_thread(
             [hp, mesh, nn, nc, nf, flags, &copy_err]
             {
@@ -485,6 +539,27 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
                 copy_err = std::current_exception();
               }
             });
+        // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
+        bool dg_identity = true;
+        const int ndg_chk = t->ndg;
+        std::thread dgmap_thread(
+            [mesh, nc, ndg_chk, &dg_identity, &dgmap_err]
+            {
+              try
+              {
+                if (mesh->dg_dofmap)
+                  for (size_t i = 0; i < nc * (size_t)ndg_chk; ++i)
+                    if (mesh->dg_dofmap[i] != (int32_t)i)
+                    {
+                      dg_identity = false;
+                      break;
+                    }
+              }
+              catch (...)
+              {
+                dgmap_err = std::current_exception();
+              }
+            });
         struct Joiner
         {
           std::thread &a, &b;
@@ -495,7 +570,19 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
             if (b.joinable())
               b.join();
           }
-        } joiner{colour_thread, copy_thread};
+        } joiner{copy_thread, dgmap_thread};
+        h->d_x.alloc(nn * 3);
+        h->d_cell_node.alloc(nc * 3);
+        h->d_cell_fct.alloc(nc * 3);
+        h->d_fct_node.alloc(nf * 2);
+        h->d_fct_cell_off.alloc(nf + 1);
+        h->d_fct_cell.alloc(mesh->fct_cell_off[nf]);
+        h->d_node_cell_off.alloc(nn + 1);
+        h->d_node_cell.alloc(mesh->node_cell_off[nn]);
+        h->d_node_fct_off.alloc(nn + 1);
+        h->d_node_fct.alloc(mesh->node_fct_off[nn]);
+        h->d_fct_perms.alloc(nc * 3);
+        tm.lap("create: mesh allocations");
         h->d_x.upload(mesh->x, nn * 3);
         h->d_cell_node.upload(mesh->cell_node, nc * 3);
         h->d_cell_fct.upload(mesh->cell_fct, nc * 3);
@@ -508,20 +595,15 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
         h->d_fct_perms.upload(mesh->fct_perms, nc * 3);
         tm.lap("create: mesh upload");
-        // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
-        h->dg_identity = true;
-        if (mesh->dg_dofmap)
-        {
-          for (size_t i = 0; i < nc * (size_t)t->ndg; ++i)
-            if (mesh->dg_dofmap[i] != (int32_t)i)
-            {
-              h->dg_identity = false;
-              break;
-            }
-          if (!h->dg_identity)
-            h->d_dg_dofmap.upload(mesh->dg_dofmap, nc * t->ndg);
-        }
-
+        // colouring (device) + launch order (host threads) while the topology copies / dofmap check run
+        colour_patches(h.get());
+        tm.lap("create: colouring + launch order");
+        dgmap_thread.join();
+        if (dgmap_err)
+          std::rethrow_exception(dgmap_err);
+        h->dg_identity = dg_identity;
+        if (!h->dg_identity)
+          h->d_dg_dofmap.upload(mesh->dg_dofmap, nc * t->ndg);
         tm.lap("create: dg dofmap check");
         // reference-matrix tables -> one flat device block
         std::vector<double> flat;
@@ -636,10 +718,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         tm.lap("create: tables");
         launch_compute_cellJ(h.get());
         tm.lap("create: cell Jacobians");
-        colour_thread.join();
         copy_thread.join();
-        if (colour_err)
-          std::rethrow_exception(colour_err);
         if (copy_err)
           std::rethrow_exception(copy_err);
         // the caller's arrays are not referenced after eqlb_create: stress handles switch to their copies
@@ -648,7 +727,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
                      h->h_node_fct_off.data(), h->h_node_fct.data(), h->h_fct_node.data()};
         else
           h->topo = {};
-        tm.lap("create: wait for colouring / topology copies");
+        tm.lap("create: wait for topology copies");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         *out = h.release();
       });
@@ -1224,6 +1303,8 @@ int eqlb_local_project(eqlb_handle* h, int nfun, const double* const* qvals, dou
       {
         if (!h || !qvals || !out || nfun < 1)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_local_project: bad argument");
+        if (!h->dg_identity)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_local_project: the DG_p functions must use the DOLFINx layout cell*ndg + i (eqlb_mesh.dg_dofmap)");
         const size_t nin = (size_t)h->ncell * h->nq, nout = (size_t)h->ncell * h->ndg;
         std::vector<const double*> dq(nfun);
         std::vector<double*> dout(nfun);
@@ -1416,6 +1497,8 @@ void run_primal(eqlb_handle* h, bool ev, const double* const* uh, const double* 
 {
   if (!h || !uh || !fh || !sigma)
     throw EqlbError(EQLB_ERR_INPUT, "eqlb_*_run_primal: null argument");
+  if (!h->dg_identity)
+    throw EqlbError(EQLB_ERR_INPUT, "eqlb_*_run_primal: the DG_p functions must use the DOLFINx layout cell*ndg + i (eqlb_mesh.dg_dofmap)");
   if (!h->bcs_set)
     throw EqlbError(EQLB_ERR_STATE, "boundary conditions not set (eqlb_set_bcs)");
   check_memspace3(memspace, "eqlb_*_run_primal");
@@ -1488,6 +1571,8 @@ int eqlb_project_primal(eqlb_handle* h, int nfun, const double* const* uh, const
       {
         if (!h || nfun < 1)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_project_primal: bad argument");
+        if (!h->dg_identity)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_project_primal: the DG_p functions must use the DOLFINx layout cell*ndg + i (eqlb_mesh.dg_dofmap)");
         if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_project_primal: memspace must be EQLB_HOST or EQLB_DEVICE");
         const bool host = memspace == EQLB_HOST;
@@ -1528,6 +1613,8 @@ int eqlb_estimate_poisson(eqlb_handle* h, int nfun, const double* const* sigma, 
       {
         if (!h || nfun < 1 || !sigma || !eta_sig2 || !eta_osc2)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_poisson: bad argument");
+        if (!h->dg_identity)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_poisson: the DG_p functions must use the DOLFINx layout cell*ndg + i (eqlb_mesh.dg_dofmap)");
         if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_poisson: memspace must be EQLB_HOST or EQLB_DEVICE");
         const bool host = memspace == EQLB_HOST;
@@ -1558,6 +1645,8 @@ int eqlb_estimate_elasticity(eqlb_handle* h, const double* const* dsig, const do
       {
         if (!h || !dsig || !eta)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_elasticity: bad argument");
+        if (!h->dg_identity)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_elasticity: the DG_p functions must use the DOLFINx layout cell*ndg + i (eqlb_mesh.dg_dofmap)");
         if (memspace != EQLB_HOST && memspace != EQLB_DEVICE)
           throw EqlbError(EQLB_ERR_INPUT, "eqlb_estimate_elasticity: memspace must be EQLB_HOST or EQLB_DEVICE");
         const bool host = memspace == EQLB_HOST;

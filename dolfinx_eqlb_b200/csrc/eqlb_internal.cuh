@@ -66,6 +66,11 @@ bool host_is_pinned(const void* p);
 void eqlb_h2d(void* dst_dev, const void* src_host, size_t bytes);
 void eqlb_d2h(void* dst_host, const void* src_dev, size_t bytes);
 
+// device memory from the stream-ordered pool (freed blocks stay cached: a new handle of the same process does not
+// pay the 1-2 ms per cudaMalloc of a fresh 50-270 MB block again); staged_copy.cu
+void* eqlb_dev_alloc(size_t bytes);
+void eqlb_dev_free(void* p);
+
 template <typename T>
 struct DevBuf
 {
@@ -78,7 +83,7 @@ struct DevBuf
   void release()
   {
     if (p)
-      cudaFree(p);
+      eqlb_dev_free(p);
     p = nullptr;
     n = 0;
   }
@@ -89,7 +94,7 @@ struct DevBuf
     release();
     if (count == 0)
       return;
-    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    p = static_cast<T*>(eqlb_dev_alloc(count * sizeof(T)));
     n = count;
   }
   void upload(const T* host, size_t count)
@@ -272,6 +277,8 @@ struct eqlb_handle
 
 // kernels launchers (defined in the .cu files)
 void launch_compute_cellJ(eqlb_handle* h);
+// exact sequential first-fit colouring, computed on the device (patch_builder.cu)
+int device_greedy_colouring(eqlb_handle* h, const uint8_t* h_skip, std::vector<int32_t>& colour);
 void launch_patch_builder(eqlb_handle* h, int32_t* d_ncells_out, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inodes,
                           int8_t* d_fcts_local, int8_t* d_type, uint8_t* d_reversed, uint8_t* d_reversion);
 void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, int8_t* d_bmarkers, int ndpc, int hzmax);

@@ -1328,7 +1328,7 @@ void launch_patch_t(eqlb_handle* h, const double* const* dG, const double* const
       static const bool stress_fast = getenv("EQLB_STRESS_GENERIC") == nullptr;
       const bool k2ok = (K == 2 && NDG == 3 && h->d_k2tab.p);
       const bool k1ok = (K == 1 && NDG == 1 && h->d_k1tab.p);
-      if (!(h->flags & EQLB_FLAG_GENERIC) && !h->h_seg_subs[c].empty()
+      if (!(h->flags & EQLB_FLAG_GENERIC) && h->dg_identity && !h->h_seg_subs[c].empty()  // (the lane-per-cell kernels read G, f in the DOLFINx layout)
           && (stress ? (k2ok && stress_fast && !EV) : (k1ok || k2ok || (kw_supported(K, NDG) && h->d_kwtab.p))))
       {
         // specialised kernels for the eligible head of the segment (one launch per lane class), generic

@@ -105,7 +105,7 @@ class _Problem:
                  host_pipeline=False, generic=False, interface_first=False):
         self.lib = cabi.load_library()
         self.mesh, self.tables, self.nrhs = mesh, tables, nrhs
-        self._pm = cabi.PackedMesh(mesh, tables.ndg, node_owned)
+        self._pm = cabi.PackedMesh(mesh, tables.ndg, node_owned, identity_dg_as_null=True)
         self._pt = cabi.PackedTables(tables)
         flags = ((1 if stress else 0) | (2 if atomic else 0) | (4 if generic else 0) | (16 if host_pipeline else 0)
                  | (32 if interface_first else 0))

@@ -84,7 +84,8 @@ typedef struct eqlb_mesh {
   const int32_t*  node_fct;
   const uint8_t*  fct_perms;      /* [ncell*3]  topology().get_facet_permutations()  */
   const uint32_t* cell_perm_info; /* [ncell]    topology().get_cell_permutation_info() */
-  const int32_t*  dg_dofmap;      /* [ncell*ndg] dofmap of the DG_p space of G and f */
+  const int32_t*  dg_dofmap;      /* [ncell*ndg] dofmap of the DG_p space of G and f; NULL = the DOLFINx layout
+                                     cell*ndg + i (any other map: generic patch kernel, no projection calls) */
   const uint8_t*  node_owned;     /* [nnode] 1 = equilibrate the patch of this node (index_map(0) owned
                                      nodes, `se/reconstruction.hpp:90`); NULL = all nodes          */
 } eqlb_mesh;

@@ -223,3 +223,58 @@ def test_too_many_cells_is_an_error():
     z = [np.zeros(m.ncell * T.ndg)]
     with pytest.raises(RuntimeError, match="more than 32 cells"):
         eqlb.FluxEqlbSE(2, m, z, [np.zeros(m.ncell * T.ndg * 2)])
+
+
+@pytest.mark.parametrize("kind,n,scramble", [("crossed", 24, None), ("crossed", 17, 3), ("randdiag", 40, 2), ("fan", 8, 1)])
+def test_device_colouring_is_the_sequential_first_fit(kind, n, scramble):
+    """The colouring computed on the device (wavefront of dependent decisions, `greedy_colour_kernel`) is exactly
+    the sequential first-fit colouring in vertex order - evaluated here by a plain Python loop."""
+    from common import make_mesh
+    from dolfinx_eqlb_b200 import tables as tb
+
+    m = make_mesh(kind, n, scramble)
+    T = tb.make_tables(1)
+    z = [np.zeros(m.ncell * T.ndg)]
+    eq = eqlb.FluxEqlbSE(1, m, z, [np.zeros(m.ncell * T.ndg * 2)])
+    eq.set_boundary_conditions([m.bfct.astype(np.int32)], [[]])
+    got = eq.problem.patch_maps()
+    colour = -np.ones(m.nnode, dtype=np.int64)
+    for v in range(m.nnode):
+        cells = m.node_cell[m.node_cell_off[v]:m.node_cell_off[v + 1]]
+        used = set(colour[m.cell_node[cells].ravel()].tolist())
+        c = 0
+        while c in used:
+            c += 1
+        colour[v] = c
+    assert np.array_equal(got["colour"], colour)
+    assert got["ncolours"] == colour.max() + 1
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_permuted_dg_dofmap(k):
+    """`eqlb_mesh.dg_dofmap` other than the DOLFINx layout: G and f are read through the map (generic kernel);
+    same fluxes as the identity layout with the vectors permuted back"""
+    from common import PoissonCase, make_mesh
+
+    m = make_mesh("crossed", 6, 3, perturb=0.2)
+    case = PoissonCase(m, k, [[1, 4]], seed=2, galerkin=False)
+    ndg = case.T.ndg
+    ref = {}
+    for cls in (eqlb.FluxEqlbSE, eqlb.FluxEqlbEV):
+        eq = cls(k, m, case.F, case.G)
+        eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+        eq.equilibrate_fluxes()
+        ref[cls] = np.array(eq.list_flux[0])
+    perm = np.random.default_rng(0).permutation(m.ncell * ndg).astype(np.int32)  # dof of (cell, i) = perm[cell*ndg + i]
+    Fp, Gp = np.zeros_like(case.F[0]), np.zeros_like(case.G[0])
+    Fp[perm] = case.F[0]
+    Gp.reshape(-1, 2)[perm] = case.G[0].reshape(-1, 2)
+    m.dg_dofmap = perm.reshape(m.ncell, ndg)
+    try:
+        for cls in (eqlb.FluxEqlbSE, eqlb.FluxEqlbEV):
+            eq = cls(k, m, [Fp], [Gp])
+            eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+            eq.equilibrate_fluxes()
+            assert np.abs(eq.list_flux[0] - ref[cls]).max() < 1e-11 * np.abs(ref[cls]).max()
+    finally:
+        del m.dg_dofmap

@@ -135,7 +135,7 @@ CONFIGS = {
     4: dict(path="se", k=2, nrhs=3, n=4096, stress=True, neumann=[]),
 }
 
-KERNEL_SOURCES = ["patch_k2_kernel.cu", "patch_kw_kernel.cu", "patch_k1_kernel.cu", "se_kernel.cu", "eqlb_internal.cuh"]
+KERNEL_SOURCES = ["patch_k2_kernel.cu", "patch_kw_kernel.cu", "patch_k1_kernel.cu", "se_kernel.cu"]  # the files that hold the patch kernels
 
 
 def kernel_source_hash():
@@ -152,7 +152,7 @@ def kernel_source_hash():
 
 def ncu_record(key):
     """ncu evidence of the dominant kernel of a workload (dram bytes per launch, executed FP64 flop per
-    patch) from profiles/ncu_kernels.json (written by tools/ncu_summary.py from a `ncu --set full`
+    patch) from profiles/ncu_kernels.json (written by tools/ncu_to_json.py from a `ncu --set full`
     capture of this very bench command); None if there is no capture or it is stale."""
     p = os.path.join(ROOT, "profiles", "ncu_kernels.json")
     if not os.path.exists(p):

@@ -112,15 +112,23 @@ void colour_patches(eqlb_handle* h)
   }
   else
   {
-    // the same colouring, computed on the device from the uploaded connectivity (patch_builder.cu)
-    std::vector<uint8_t> skip(n);
-    bool any = false;
-    for (int z = 0; z < n; ++z)
+    // the same colouring, computed on the device from the uploaded connectivity (patch_builder.cu); eqlb_create
+    // has queued the kernel already (h->colouring_job) and uploaded the rest of the mesh meanwhile
+    std::shared_ptr<ColouringJob> job = h->colouring_job;
+    h->colouring_job.reset();
+    if (!job)
     {
-      skip[z] = (!h->h_owned[z] || h->h_grouped[z]) ? 1 : 0;
-      any = any || skip[z];
+      std::vector<uint8_t> skip;
+      if (h->nactive < n || ngrouped > 0)
+      {
+        skip.resize(n);
+        for (int z = 0; z < n; ++z)
+          skip[z] = (!h->h_owned[z] || h->h_grouped[z]) ? 1 : 0;
+      }
+      job = device_greedy_colouring_start(h, skip.empty() ? nullptr : skip.data());
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));  // `skip` is read by an asynchronous copy
     }
-    ncol = device_greedy_colouring(h, any ? skip.data() : nullptr, h->h_colour);
+    ncol = device_greedy_colouring_finish(h, *job, h->h_colour);
   }
   StageTimer ctm;
   ctm.t0 = t_enter;
@@ -202,26 +210,60 @@ void colour_patches(eqlb_handle* h)
       x.join();
   }
   ctm.lap("  colouring: segment / lane class");
-  for (int z = 0; z < n; ++z)
-    if (vseg[z] >= 0)
-      h->h_colour_off[vseg[z] + 1]++;
+  // counting sort of the active patches by (segment, lane class), vertex order within a class; the histogram and
+  // the scatter run on host threads over contiguous vertex ranges (same result for any thread count)
+  const int nthr_o = n > (1 << 16) ? std::max(1, std::min(6, (int)std::thread::hardware_concurrency() / 2)) : 1;
+  const size_t nkey = 4 * (size_t)h->nseg;
+  std::vector<int32_t> hist((size_t)nthr_o * nkey, 0);  // [thread][segment][raw class 0..3]
+  auto zrange = [&](int t, int& z0, int& z1)
+  {
+    z0 = (int)((long)n * t / nthr_o);
+    z1 = (int)((long)n * (t + 1) / nthr_o);
+  };
+  auto run_threads = [&](auto&& fn)
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthr_o; ++t)
+      th.emplace_back(fn, t);
+    fn(0);
+    for (auto& x : th)
+      x.join();
+  };
+  run_threads(
+      [&](int t)
+      {
+        int z0, z1;
+        zrange(t, z0, z1);
+        int32_t* hh = &hist[(size_t)t * nkey];
+        for (int z = z0; z < z1; ++z)
+          if (vseg[z] >= 0)
+            hh[4 * vseg[z] + vcls[z]]++;
+      });
+  // class sizes per segment; a lane class with few members joins the next wider one (saves a launch)
+  std::vector<int32_t> ccount(3 * (size_t)h->nseg, 0);
+  for (int sg = 0; sg < h->nseg; ++sg)
+  {
+    int32_t tot = 0;
+    for (int t = 0; t < nthr_o; ++t)
+      for (int cl = 0; cl < 4; ++cl)
+      {
+        const int32_t v = hist[(size_t)t * nkey + 4 * sg + cl];
+        tot += v;
+        if (cl < 3)
+          ccount[3 * sg + cl] += v;
+      }
+    h->h_colour_off[sg + 1] = tot;
+  }
   h->h_colour_off[0] = ngrouped;  // grouped patches occupy the head of h_order
   for (int c = 0; c < h->nseg; ++c)
     h->h_colour_off[c + 1] += h->h_colour_off[c];
-  std::vector<int32_t> pos(h->h_colour_off.begin(), h->h_colour_off.end() - 1);
   h->h_order.resize(h->nactive);
-  // within a segment: lane classes 4 / 8 / 16 first, then the rest; a class with few members joins the next
-  // wider one (saves a launch)
-  std::vector<int32_t> ccount(3 * (size_t)h->nseg, 0);
-  for (int z = 0; z < n; ++z)
-    if (vseg[z] >= 0 && vcls[z] < 3)
-      ccount[3 * vseg[z] + vcls[z]]++;
-  std::vector<int8_t> cmap(3 * (size_t)h->nseg);
+  std::vector<int8_t> cmap(4 * (size_t)h->nseg);
   for (int sg = 0; sg < h->nseg; ++sg)
   {
     int32_t* cc = &ccount[3 * sg];
-    int8_t* cm = &cmap[3 * sg];
-    cm[0] = 0, cm[1] = 1, cm[2] = 2;
+    int8_t* cm = &cmap[4 * sg];
+    cm[0] = 0, cm[1] = 1, cm[2] = 2, cm[3] = 3;
     const int thr = std::max(8192, (cc[0] + cc[1] + cc[2]) / 16);
     if (cc[1] > 0 && cc[1] < thr && cc[2] > 0)
       cm[1] = 2, cc[2] += cc[1], cc[1] = 0;
@@ -233,26 +275,41 @@ void colour_patches(eqlb_handle* h)
   }
   h->h_colour_fast.assign(h->nseg, 0);
   h->h_seg_subs.assign(h->nseg, {});
-  std::vector<int32_t> start(4 * (size_t)h->nseg);
+  // start of (segment, merged class, thread): classes in order, threads in order within a class
+  std::vector<int32_t> start((size_t)nthr_o * nkey, 0);
   for (int sg = 0; sg < h->nseg; ++sg)
   {
-    int32_t at = pos[sg];
-    for (int cl = 0; cl < 3; ++cl)
+    int32_t at = h->h_colour_off[sg];
+    for (int cl = 0; cl < 4; ++cl)
     {
-      start[4 * sg + cl] = at;
-      if (ccount[3 * sg + cl] > 0)
-        h->h_seg_subs[sg].push_back({at, ccount[3 * sg + cl], 4 << cl, -1});
-      at += ccount[3 * sg + cl];
-      h->h_colour_fast[sg] += ccount[3 * sg + cl];
+      const int32_t first = at;
+      for (int t = 0; t < nthr_o; ++t)
+      {
+        start[(size_t)t * nkey + 4 * sg + cl] = at;
+        for (int raw = 0; raw < 4; ++raw)
+          if (cmap[4 * sg + raw] == cl)
+            at += hist[(size_t)t * nkey + 4 * sg + raw];
+      }
+      if (cl < 3 && at > first)
+      {
+        h->h_seg_subs[sg].push_back({first, at - first, 4 << cl, -1});
+        h->h_colour_fast[sg] += at - first;
+      }
     }
-    start[4 * sg + 3] = at;
   }
-  for (int z = 0; z < n; ++z)  // vertex order within every class: the order is deterministic
-    if (vseg[z] >= 0)
-    {
-      const int lc = vcls[z], sg = vseg[z];
-      h->h_order[start[4 * sg + (lc < 3 ? cmap[3 * sg + lc] : 3)]++] = z;
-    }
+  run_threads(
+      [&](int t)
+      {
+        int z0, z1;
+        zrange(t, z0, z1);
+        int32_t* st = &start[(size_t)t * nkey];
+        for (int z = z0; z < z1; ++z)
+          if (vseg[z] >= 0)
+          {
+            const int sg = vseg[z];
+            h->h_order[st[4 * sg + cmap[4 * sg + vcls[z]]]++] = z;
+          }
+      });
 
   ctm.lap("  colouring: launch order");
   // result ranges of the host pipeline: a range of DOFs can go back to the host after the
@@ -583,21 +640,63 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->d_node_fct.alloc(mesh->node_fct_off[nn]);
         h->d_fct_perms.alloc(nc * 3);
         tm.lap("create: mesh allocations");
-        h->d_x.upload(mesh->x, nn * 3);
+        // connectivity of the colouring first: its kernel runs while the other arrays are uploaded
         h->d_cell_node.upload(mesh->cell_node, nc * 3);
-        h->d_cell_fct.upload(mesh->cell_fct, nc * 3);
-        h->d_fct_node.upload(mesh->fct_node, nf * 2);
-        h->d_fct_cell_off.upload(mesh->fct_cell_off, nf + 1);
-        h->d_fct_cell.upload(mesh->fct_cell, mesh->fct_cell_off[nf]);
         h->d_node_cell_off.upload(mesh->node_cell_off, nn + 1);
         h->d_node_cell.upload(mesh->node_cell, mesh->node_cell_off[nn]);
-        h->d_node_fct_off.upload(mesh->node_fct_off, nn + 1);
-        h->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
-        h->d_fct_perms.upload(mesh->fct_perms, nc * 3);
-        tm.lap("create: mesh upload");
+        static const bool host_col = getenv("EQLB_HOST_COLOURING") && atoi(getenv("EQLB_HOST_COLOURING")) != 0;
+        std::vector<uint8_t> skip;
+        if (!host_col)
+        {
+          if (h->nactive < (int)nn)
+          {
+            skip.resize(nn);
+            for (size_t z = 0; z < nn; ++z)
+              skip[z] = h->h_owned[z] ? 0 : 1;
+          }
+          h->colouring_job = device_greedy_colouring_start(h.get(), skip.empty() ? nullptr : skip.data());
+        }
+        // the other arrays travel on a second host thread while this one waits for the colours and sorts the
+        // patches into launch order (the buffers are allocated, the copies go through the staging pool)
+        std::exception_ptr upload_err;
+        const int dev_id = h->device;
+        std::thread upload_thread(
+            [hp, mesh, nn, nc, nf, dev_id, &upload_err]
+            {
+              try
+              {
+                CUDA_CHECK(cudaSetDevice(dev_id));
+                hp->d_x.upload(mesh->x, nn * 3);
+                hp->d_cell_fct.upload(mesh->cell_fct, nc * 3);
+                hp->d_fct_node.upload(mesh->fct_node, nf * 2);
+                hp->d_fct_cell_off.upload(mesh->fct_cell_off, nf + 1);
+                hp->d_fct_cell.upload(mesh->fct_cell, mesh->fct_cell_off[nf]);
+                hp->d_node_fct_off.upload(mesh->node_fct_off, nn + 1);
+                hp->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
+                hp->d_fct_perms.upload(mesh->fct_perms, nc * 3);
+              }
+              catch (...)
+              {
+                upload_err = std::current_exception();
+              }
+            });
+        struct Joiner1
+        {
+          std::thread& a;
+          ~Joiner1()
+          {
+            if (a.joinable())
+              a.join();
+          }
+        } joiner_up{upload_thread};
+        tm.lap("create: colouring connectivity upload");
         // colouring (device) + launch order (host threads) while the topology copies / dofmap check run
         colour_patches(h.get());
         tm.lap("create: colouring + launch order");
+        upload_thread.join();
+        if (upload_err)
+          std::rethrow_exception(upload_err);
+        tm.lap("create: wait for the mesh upload");
         dgmap_thread.join();
         if (dgmap_err)
           std::rethrow_exception(dgmap_err);

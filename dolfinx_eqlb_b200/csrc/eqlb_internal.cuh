@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -170,6 +171,8 @@ struct PatchView
   const int4* rec;
 };
 
+struct ColouringJob;  // patch_builder.cu
+
 struct eqlb_handle
 {
   int device = 0;
@@ -248,6 +251,7 @@ struct eqlb_handle
     int32_t first, count, lanes;  // range in h_order, lanes per patch (4, 8, 16)
     int64_t recoff;               // offset of its lane records in d_prec
   };
+  std::shared_ptr<ColouringJob> colouring_job;  // queued by eqlb_create, consumed by colour_patches
   std::vector<std::vector<FastSub>> h_seg_subs;  // [nseg] (empty: no lane-per-cell launch)
   int nsub = 0;
   DevBuf<int64_t> d_seginfo;            // [nsub][4] first, count, lanes, recoff
@@ -278,7 +282,9 @@ struct eqlb_handle
 // kernels launchers (defined in the .cu files)
 void launch_compute_cellJ(eqlb_handle* h);
 // exact sequential first-fit colouring, computed on the device (patch_builder.cu)
-int device_greedy_colouring(eqlb_handle* h, const uint8_t* h_skip, std::vector<int32_t>& colour);
+struct ColouringJob;
+std::shared_ptr<ColouringJob> device_greedy_colouring_start(eqlb_handle* h, const uint8_t* h_skip);
+int device_greedy_colouring_finish(eqlb_handle* h, ColouringJob& job, std::vector<int32_t>& colour);
 void launch_patch_builder(eqlb_handle* h, int32_t* d_ncells_out, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inodes,
                           int8_t* d_fcts_local, int8_t* d_type, uint8_t* d_reversed, uint8_t* d_reversion);
 void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, int8_t* d_bmarkers, int ndpc, int hzmax);

@@ -906,38 +906,66 @@ greedy_colour_kernel(int n, const int32_t* __restrict__ node_cell_off, const int
 }
 } // namespace
 
-// colours of all vertices (host vector, -1 for skipped vertices); returns the number of colours
-int device_greedy_colouring(eqlb_handle* h, const uint8_t* h_skip, std::vector<int32_t>& colour)
+// Colours of all vertices (-1 for skipped vertices).  Two halves so that the caller can overlap the kernel with
+// other work (eqlb_create uploads the rest of the mesh meanwhile): `start` queues the kernel on the handle's
+// stream, `finish` fetches the result into the host vector and returns the number of colours.
+struct ColouringJob
 {
-  const int n = h->nnode;
-  colour.assign(n, -1);
-  if (n == 0)
-    return 0;
   DevBuf<int> d_col;
-  DevBuf<unsigned> d_ctl;  // [ticket, status]
+  DevBuf<unsigned> d_ctl;  // [ticket, status, max colour + 1]
   DevBuf<uint8_t> d_skip;
-  d_col.alloc(n);
-  d_ctl.alloc(2);
-  d_ctl.zero(h->stream);
+};
+
+namespace
+{
+__global__ void max_colour_kernel(const int* __restrict__ colour, int n, unsigned* out)
+{
+  int m = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = max(m, colour[i] + 1);
+  for (int o = 16; o; o >>= 1)
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0)
+    atomicMax(out, (unsigned)m);
+}
+} // namespace
+
+std::shared_ptr<ColouringJob> device_greedy_colouring_start(eqlb_handle* h, const uint8_t* h_skip)
+{
+  auto job = std::make_shared<ColouringJob>();
+  const int n = h->nnode;
+  if (n == 0)
+    return job;
+  job->d_col.alloc(n);
+  job->d_ctl.alloc(4);
+  job->d_ctl.zero(h->stream);
   if (h_skip)
   {
-    d_skip.alloc(n);
-    CUDA_CHECK(cudaMemcpyAsync(d_skip.p, h_skip, n, cudaMemcpyHostToDevice, h->stream));
+    job->d_skip.alloc(n);
+    CUDA_CHECK(cudaMemcpyAsync(job->d_skip.p, h_skip, n, cudaMemcpyHostToDevice, h->stream));
   }
-  fill_int_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_col.p, n, -2);
+  fill_int_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(job->d_col.p, n, -2);
   CUDA_CHECK(cudaGetLastError());
   greedy_colour_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_node_cell_off.p, h->d_node_cell.p, h->d_cell_node.p,
-                                                               h_skip ? d_skip.p : nullptr, d_col.p, d_ctl.p,
-                                                               reinterpret_cast<int*>(d_ctl.p + 1));
+                                                               h_skip ? job->d_skip.p : nullptr, job->d_col.p, job->d_ctl.p,
+                                                               reinterpret_cast<int*>(job->d_ctl.p + 1));
   CUDA_CHECK(cudaGetLastError());
-  unsigned ctl[2] = {0, 0};
-  CUDA_CHECK(cudaMemcpyAsync(ctl, d_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_CHECK(cudaMemcpyAsync(colour.data(), d_col.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  max_colour_kernel<<<296, 256, 0, h->stream>>>(job->d_col.p, n, job->d_ctl.p + 2);
+  CUDA_CHECK(cudaGetLastError());
+  return job;
+}
+
+int device_greedy_colouring_finish(eqlb_handle* h, ColouringJob& job, std::vector<int32_t>& colour)
+{
+  const int n = h->nnode;
+  colour.resize(n);
+  if (n == 0)
+    return 0;
+  unsigned ctl[4] = {0, 0, 0, 0};
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  CUDA_CHECK(cudaMemcpy(ctl, job.d_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost));
+  eqlb_d2h(colour.data(), job.d_col.p, (size_t)n * sizeof(int));
   if (ctl[1] != 0)
     throw EqlbError(EQLB_ERR_CUDA, "device colouring made no progress (EQLB_HOST_COLOURING=1 selects the host algorithm)");
-  int ncol = 0;
-  for (int z = 0; z < n; ++z)
-    ncol = std::max(ncol, colour[z] + 1);
-  return ncol;
+  return (int)ctl[2];
 }

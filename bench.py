@@ -371,6 +371,9 @@ def halo_check(args, rank, world, dist_mod):
         hx = dd.HaloExchange(loc, gid, device="cuda")
     hx.apply(xs)
     torch.cuda.synchronize()
+    # the host-buffer route of the end-to-end leg: halo sum on the handle's staged device copy, shared DOFs refreshed
+    # in the host vectors (dist.HostHaloUpdate)
+    dd.HostHaloUpdate(hx).finish(leq.problem, args.path == "ev", leq.list_flux)
     # compared: the DOFs of all local cells with at least one owned vertex (a rank's copy of the other halo
     # cells - e.g. the bottom triangles of the halo row - receives no contribution and is never read)
     live_c = part.node_owned[lm.cell_node].any(axis=1)
@@ -378,19 +381,19 @@ def halo_check(args, rank, world, dist_mod):
     live_f[lm.cell_fct[live_c].ravel()] = True
     err = 0.0
     for r in range(nrhs):
-        got = xs[r].cpu().numpy()
         ref = geq.list_flux[r]
-        if args.path == "se":
-            want = ref.reshape(gm.ncell, T.nrt)[cg]
-            d = np.abs(got.reshape(lm.ncell, T.nrt) - want)[live_c]
-        else:
-            ncd = k * k - k
-            wf = ref[: gm.nfct * k].reshape(gm.nfct, k)[l2g_f]
-            wc = ref[gm.nfct * k :].reshape(gm.ncell, ncd)[cg]
-            want = np.concatenate([wf.ravel(), wc.ravel()])
-            d = np.concatenate([np.abs(got[: lm.nfct * k].reshape(lm.nfct, k) - wf)[live_f].ravel(),
-                                np.abs(got[lm.nfct * k :].reshape(lm.ncell, ncd) - wc)[live_c].ravel()])
-        err = max(err, float(d.max() / max(np.abs(want).max(), 1e-300)))
+        for got in (xs[r].cpu().numpy(), np.asarray(leq.list_flux[r])):
+            if args.path == "se":
+                want = ref.reshape(gm.ncell, T.nrt)[cg]
+                d = np.abs(got.reshape(lm.ncell, T.nrt) - want)[live_c]
+            else:
+                ncd = k * k - k
+                wf = ref[: gm.nfct * k].reshape(gm.nfct, k)[l2g_f]
+                wc = ref[gm.nfct * k :].reshape(gm.ncell, ncd)[cg]
+                want = np.concatenate([wf.ravel(), wc.ravel()])
+                d = np.concatenate([np.abs(got[: lm.nfct * k].reshape(lm.nfct, k) - wf)[live_f].ravel(),
+                                    np.abs(got[lm.nfct * k :].reshape(lm.ncell, ncd) - wc)[live_c].ravel()])
+            err = max(err, float(d.max() / max(np.abs(want).max(), 1e-300)))
     t = torch.tensor([err], device="cuda", dtype=torch.float64)
     dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
     if hasattr(hx, "close"):
@@ -601,16 +604,14 @@ def main():
         if rc != 0:
             raise RuntimeError(lib.eqlb_last_error().decode())
 
+    host_halo = dd.HostHaloUpdate(hx) if world > 1 else None
+
     def step_host():
         if world > 1:
-            # EQLB_HOST_IN: host inputs staged in, flux stays on the device for the halo sum
-            for d in dS:
-                d.zero_()
-            run_host(pS, 3)
-            hx.apply(dS)
-            for d, h_ in zip(dS, hS):
-                h_.copy_(d, non_blocking=True)
-            torch.cuda.synchronize()
+            # staged call (copy-in / kernels / copy-out of finished ranges) as at N = 1, then the halo sum on the
+            # device copy of the flux and a refresh of the few shared DOFs in the host vectors
+            run_host(qS, 2)
+            host_halo.finish(hprob, args.path == "ev", hS)
             return
         # EQLB_HOST_ZEROED: the flux starts from zero as in the reference's equilibrate_fluxes
         run_host(qS, 2)

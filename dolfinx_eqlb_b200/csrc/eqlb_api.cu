@@ -1193,6 +1193,22 @@ int eqlb_set_part(eqlb_handle* h, int part)
       });
 }
 
+int eqlb_get_staged_flux(eqlb_handle* h, int r, int is_ev, double** device_ptr, int64_t* n)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !device_ptr || r < 0 || r >= h->nrhs)
+          throw EqlbError(EQLB_ERR_INPUT, "eqlb_get_staged_flux: bad argument");
+        const size_t nS = is_ev ? (size_t)h->nfct * h->k + (size_t)h->ncell * (h->k * h->k - h->k) : (size_t)h->ncell * h->nrt;
+        if (h->d_stage_sigma.n < nS * (size_t)h->nrhs)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_get_staged_flux: no host-buffer call (EQLB_HOST / EQLB_HOST_ZEROED) has run on this handle");
+        *device_ptr = h->d_stage_sigma.p + (size_t)r * nS;
+        if (n)
+          *n = (int64_t)nS;
+      });
+}
+
 // Common driver of eqlb_se_run / eqlb_ev_run: device pointers are used in place; host
 // pointers are staged, either in one piece or - with EQLB_FLAG_HOST_PIPELINE - stage by
 // stage on three streams so that both PCIe directions and the SMs work at the same time.

@@ -321,3 +321,61 @@ class P2PHaloExchange:
                 self.h = None
         except Exception:
             pass
+
+
+class _RawCuda:
+    """a device pointer as an object torch can wrap without copying (`__cuda_array_interface__`)"""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def staged_flux_tensors(problem, is_ev: bool):
+    """CUDA tensors aliasing the device copies of the flux vectors written by the last host-buffer call of the
+    handle (`eqlb_get_staged_flux`); valid until the next call."""
+    import ctypes as C
+
+    import torch
+
+    out = []
+    for r in range(problem.nrhs):
+        ptr, n = C.c_void_p(), C.c_int64()
+        if problem.lib.eqlb_get_staged_flux(problem.h, r, 1 if is_ev else 0, C.byref(ptr), C.byref(n)) != 0:
+            raise RuntimeError(problem.lib.eqlb_last_error().decode())
+        out.append(torch.as_tensor(_RawCuda(ptr.value, n.value), device="cuda"))
+    return out
+
+
+class HostHaloUpdate:
+    """Host-buffer equilibration on a partitioned mesh without holding back the copy-out: the staged call writes the
+    (not yet summed) result to the host vectors stage by stage while later stages are still computed; the halo sum
+    runs on the device copy, and only the DOFs shared with other ranks - a few rows of cells next to the partition
+    boundary - are fetched again.  `shared` = union of the exchange's index lists."""
+
+    def __init__(self, hx):
+        import torch
+
+        idx = [np.asarray(i.cpu() if hasattr(i, "cpu") else i, dtype=np.int64) for _, i in hx.neigh]
+        self.shared = np.unique(np.concatenate(idx)) if idx else np.zeros(0, np.int64)
+        self.d_shared = torch.as_tensor(self.shared, device="cuda")
+        self.hx = hx
+        self._pin = None
+
+    def finish(self, problem, is_ev: bool, host_flux):
+        """after the host-buffer call: halo sum on the staged device copy, refresh of the shared DOFs in the host
+        vectors (numpy arrays or CPU tensors)"""
+        import torch
+
+        dS = staged_flux_tensors(problem, is_ev)
+        self.hx.apply(dS)
+        if self.shared.size == 0:
+            torch.cuda.current_stream().synchronize()
+            return
+        vals = torch.stack([d[self.d_shared] for d in dS])
+        if self._pin is None or self._pin.shape != vals.shape:
+            self._pin = torch.empty(vals.shape, dtype=torch.float64).pin_memory()
+        self._pin.copy_(vals, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        for r, hflux in enumerate(host_flux):
+            h_np = hflux.numpy() if hasattr(hflux, "numpy") else hflux
+            h_np[self.shared] = self._pin[r].numpy()

@@ -283,6 +283,14 @@ int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream)
 /* synchronises the stream and reports a timed-out exchange (all device-side waits are bounded: a neighbour that
  * never arrives costs seconds, not a hung GPU) */
 int eqlb_halo_status(eqlb_halo* h, void* cuda_stream);
+
+/* Device copy of the flux vector r written by the last host-buffer call (EQLB_HOST / EQLB_HOST_ZEROED) of this
+ * handle: distributed callers run the halo sum on it (eqlb_halo_apply) and fetch only the shared DOFs again,
+ * instead of holding back the whole copy-out until the exchange is done (dolfinx_eqlb_b200/dist.py
+ * `equilibrate_host`).  Valid until the next call on the handle.  The reference has no counterpart (its flux
+ * vectors are host PETSc vectors whose ghost update is PETSc's, `se/reconstruction.hpp:150-160`). */
+int eqlb_get_staged_flux(eqlb_handle* h, int r, int is_ev, double** device_ptr, int64_t* n);
+
 /* every rank must have finished its exchanges (collective barrier + device synchronisation) before any rank
  * destroys its handle: the neighbours read this rank's buffer over NVLink */
 void eqlb_halo_destroy(eqlb_halo* h);

@@ -70,7 +70,6 @@ struct Mesh
   py::array_t<std::uint32_t, py::array::c_style | py::array::forcecast> cell_perm_info;
   int nnode, ncell, nfct;
   std::map<std::tuple<int, int, int, unsigned>, std::shared_ptr<HandleEntry>> cache;
-  std::vector<std::int32_t> dg_dofmap;
 
   Mesh(darray x_, iarray cn, iarray cf, iarray fn, iarray fco, iarray fc, iarray nco, iarray nc, iarray nfo, iarray nf,
        py::array_t<std::uint8_t, py::array::c_style | py::array::forcecast> perms,
@@ -123,6 +122,24 @@ struct Function
   std::shared_ptr<FunctionSpace> V;
   darray x;
   std::string name = "u";
+  int host_calls = 0;   // equilibration calls that moved this vector over PCIe
+  bool pinned = false;  // page-locked by note_host_call
+  // A first call runs from pageable memory (the library stages the copies through its pinned pool); when a vector
+  // shows up in a second call (time loops) it is page-locked once so that the stage pipeline can take over.
+  void note_host_call()
+  {
+    if (pinned || x.nbytes() < (py::ssize_t)(4 << 20))
+      return;
+    if (++host_calls >= 2 && eqlb_pin_host(x.mutable_data(), (size_t)x.nbytes()) == EQLB_OK)
+      pinned = true;
+  }
+  ~Function()
+  {
+    if (pinned)
+      eqlb_unpin_host(x.mutable_data());
+  }
+  Function(const Function&) = delete;
+  Function& operator=(const Function&) = delete;
   Function(std::shared_ptr<FunctionSpace> V_, py::object arr) : V(std::move(V_))
   {
     if (arr.is_none())
@@ -267,10 +284,6 @@ std::shared_ptr<HandleEntry> get_handle(Mesh& m, int k, int p, int nrhs, unsigne
   if (it != m.cache.end())
     return it->second;
   Tables T(k, p);
-  const int ndg = T.t.ndg;
-  m.dg_dofmap.resize((size_t)m.ncell * ndg);
-  for (size_t i = 0; i < m.dg_dofmap.size(); ++i)
-    m.dg_dofmap[i] = (std::int32_t)i;  // DOLFINx DG layout cell * ndg + local
   eqlb_mesh em{};
   em.nnode = m.nnode;
   em.ncell = m.ncell;
@@ -287,7 +300,7 @@ std::shared_ptr<HandleEntry> get_handle(Mesh& m, int k, int p, int nrhs, unsigne
   em.node_fct = m.node_fct.data();
   em.fct_perms = m.fct_perms.data();
   em.cell_perm_info = m.cell_perm_info.data();
-  em.dg_dofmap = m.dg_dofmap.data();
+  em.dg_dofmap = nullptr;  // the holders' DG spaces use the DOLFINx layout cell * ndg + local (a DOLFINx build passes the dofmap)
   em.node_owned = nullptr;
   auto e = std::make_shared<HandleEntry>();
   check(eqlb_create(&em, &T.t, nrhs, flags, &e->h));
@@ -487,6 +500,9 @@ void se_impl(std::vector<std::shared_ptr<Function>>& flux_hdiv, std::vector<std:
     G[r] = flux_dg[r]->x.data();
     F[r] = rhs_dg[r]->x.data();
     S[r] = flux_hdiv[r]->x.mutable_data();
+    flux_dg[r]->note_host_call();
+    rhs_dg[r]->note_host_call();
+    flux_hdiv[r]->note_host_call();
   }
   py::gil_scoped_release rel;
   check(eqlb_se_run(e->h, G.data(), F.data(), S.data(), korn ? korn->x.mutable_data() : nullptr, EQLB_HOST));
@@ -669,6 +685,9 @@ PYBIND11_MODULE(cpp, mod)
           G[r] = l[r]->flux_dg->x.data();
           F[r] = l[r]->rhs_dg->x.data();
           S[r] = flux_hdiv[r]->x.mutable_data();
+          l[r]->flux_dg->note_host_call();
+          l[r]->rhs_dg->note_host_call();
+          flux_hdiv[r]->note_host_call();
         }
         const int p = degree_of(l[0]->rhs_dg);
         auto e = get_handle(m, k, p, n_rhs, EQLB_FLAG_HOST_PIPELINE);

@@ -390,6 +390,29 @@ eqlb_handle::~eqlb_handle()
     cudaStreamDestroy(s_d2h);
 }
 
+// Host copies of the connectivity around the vertices (grouping of boundary patches, re-colouring after a BC set
+// has grouped patches): fetched from the device on first use - most handles never need them (the caller's arrays
+// are not referenced after eqlb_create).
+static void ensure_host_topology(eqlb_handle* h)
+{
+  if (!h->h_node_cell_off.empty())
+    return;
+  auto fetch = [&](std::vector<int32_t>& dst, const DevBuf<int32_t>& src)
+  {
+    dst.resize(src.n);
+    eqlb_d2h(dst.data(), src.p, src.n * sizeof(int32_t));
+  };
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  fetch(h->h_node_cell_off, h->d_node_cell_off);
+  fetch(h->h_node_cell, h->d_node_cell);
+  fetch(h->h_cell_node, h->d_cell_node);
+  fetch(h->h_node_fct_off, h->d_node_fct_off);
+  fetch(h->h_node_fct, h->d_node_fct);
+  fetch(h->h_fct_node, h->d_fct_node);
+  h->topo = {h->h_node_cell_off.data(), h->h_node_cell.data(), h->h_cell_node.data(),
+             h->h_node_fct_off.data(), h->h_node_fct.data(), h->h_fct_node.data()};
+}
+
 // Shared tail of eqlb_set_bcs / eqlb_set_bcs_poly: grouping of 2-cell traction patches (host, needs the
 // facet types and node markers on the host), colouring, record buffers, device patch builder.
 static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* node_on_stress_bnd, bool upload_node_markers,
@@ -405,8 +428,12 @@ static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* n
       h->h_grouped.assign(h->nnode, 0);
       h->h_group_off.clear();
       std::vector<int32_t> gorder;
-      if ((h->flags & EQLB_FLAG_STRESS) && h->k == 2)
+      bool any_marked = false;
+      for (int z = 0; z < h->nnode && !any_marked; ++z)
+        any_marked = node_on_stress_bnd[z] != 0;
+      if ((h->flags & EQLB_FLAG_STRESS) && h->k == 2 && any_marked)
       {
+        ensure_host_topology(h);
         auto ncells_of = [&](int z) { return h->h_node_cell_off[z + 1] - h->h_node_cell_off[z]; };
         std::vector<uint8_t> perform(h->nnode, 1);
         for (int z = 0; z < h->nnode; ++z)
@@ -451,7 +478,10 @@ static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* n
         }
       }
       if (!gorder.empty() || h->h_order.empty() || h->coloured_with_groups)
+      {
+        ensure_host_topology(h);
         colour_patches(h);
+      }
       h->coloured_with_groups = !gorder.empty();
       std::copy(gorder.begin(), gorder.end(), h->h_order.begin());
     }
@@ -461,7 +491,10 @@ static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* n
       h->h_grouped.assign(h->nnode, 0);
       h->h_group_off.clear();
       if (h->coloured_with_groups || h->h_order.empty())
+      {
+        ensure_host_topology(h);
         colour_patches(h);
+      }
       h->coloured_with_groups = false;
     }
 
@@ -576,26 +609,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->topo = {mesh->node_cell_off, mesh->node_cell, mesh->cell_node, mesh->node_fct_off, mesh->node_fct, mesh->fct_node};
         std::exception_ptr copy_err, dgmap_err;
         eqlb_handle* hp = h.get();
-        std::thread copy_thread(
-            [hp, mesh, nn, nc, nf, flags, &copy_err]
-            {
-              try
-              {
-                if (flags & EQLB_FLAG_STRESS)
-                {
-                  hp->h_node_cell_off.assign(mesh->node_cell_off, mesh->node_cell_off + nn + 1);
-                  hp->h_node_cell.assign(mesh->node_cell, mesh->node_cell + mesh->node_cell_off[nn]);
-                  hp->h_cell_node.assign(mesh->cell_node, mesh->cell_node + nc * 3);
-                  hp->h_node_fct_off.assign(mesh->node_fct_off, mesh->node_fct_off + nn + 1);
-                  hp->h_node_fct.assign(mesh->node_fct, mesh->node_fct + mesh->node_fct_off[nn]);
-                  hp->h_fct_node.assign(mesh->fct_node, mesh->fct_node + nf * 2);
-                }
-              }
-              catch (...)
-              {
-                copy_err = std::current_exception();
-              }
-            });
+        std::thread copy_thread([] {});  // (topology copies of stress handles are fetched lazily, ensure_host_topology)
         // DG dofmap: identity layout (cell*ndg + i) is the DOLFINx layout; otherwise indirect
         bool dg_identity = true;
         const int ndg_chk = t->ndg;
@@ -820,12 +834,8 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         copy_thread.join();
         if (copy_err)
           std::rethrow_exception(copy_err);
-        // the caller's arrays are not referenced after eqlb_create: stress handles switch to their copies
-        if (flags & EQLB_FLAG_STRESS)
-          h->topo = {h->h_node_cell_off.data(), h->h_node_cell.data(), h->h_cell_node.data(),
-                     h->h_node_fct_off.data(), h->h_node_fct.data(), h->h_fct_node.data()};
-        else
-          h->topo = {};
+        // the caller's arrays are not referenced after eqlb_create
+        h->topo = {};
         tm.lap("create: wait for topology copies");
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         *out = h.release();

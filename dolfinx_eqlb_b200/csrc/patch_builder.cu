@@ -12,6 +12,8 @@
 // (<= 16 steps) while the ~1e6..3e7 patches are independent; all loads are 4-byte
 // gathers from CSR arrays that stay L2 resident.  The builder runs once per
 // eqlb_set_bcs, not per equilibration.
+#include <cmath>
+
 #include "eqlb_internal.cuh"
 
 namespace
@@ -823,12 +825,14 @@ void launch_se_dofmaps(eqlb_handle* h, int32_t* d_dofmap, int32_t* d_projflux, i
 // ---------------------------------------------------------------------------------------------------
 // Greedy vertex colouring on the device, EXACTLY the sequential first-fit colouring in vertex order
 // (two vertices of a cell never share a colour): vertex z takes the smallest colour not used by the
-// lower-numbered vertices of its cells.  Every thread owns one vertex and retries until its lower
-// neighbours are decided; vertices are handed out in index order by a ticket counter, so whatever a
-// thread waits for belongs to a block that has already started (resident or finished) and the lowest
-// undecided vertex can always proceed.  On meshes numbered row by row the decisions sweep the mesh as a
-// wavefront (1024^2 crossed mesh: ~2000 dependent steps, a few ms); random numberings converge in a few
-// rounds.  colour: -2 undecided, -1 no colour (vertex not owned / grouped), >= 0 colour.
+// lower-numbered vertices of its cells.  Dataflow formulation: every vertex counts its lower-numbered
+// neighbours (with the multiplicity of shared cells); a vertex whose count drops to zero is appended to a
+// ready queue; persistent threads pop vertices from the queue, colour them and decrement the counts of their
+// higher-numbered neighbours.  The parallelism is the width of the dependency graph (a whole anti-diagonal of
+// a row-numbered structured mesh), the run time its depth times a queue round trip - not limited by how many
+// vertices fit on the device at once.  A popped vertex always finds all its lower neighbours decided, so
+// the result does not depend on the schedule.  colour: -1 = no colour (vertex not owned / grouped).
+// Skipped vertices take part in the dataflow (they release their neighbours) but get no colour.
 // ---------------------------------------------------------------------------------------------------
 namespace
 {
@@ -839,10 +843,34 @@ __global__ void fill_int_kernel(int* p, int n, int v)
     p[i] = v;
 }
 
+// pending[z] = number of (cell, vertex) pairs around z with a lower-numbered vertex; ready vertices -> queue
+__global__ void colour_count_kernel(int n, const int32_t* __restrict__ node_cell_off, const int32_t* __restrict__ node_cell,
+                                    const int32_t* __restrict__ cell_node, int* pending, int* queue, unsigned* ctl)
+{
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= n)
+    return;
+  int cnt = 0;
+  for (int i = node_cell_off[z]; i < node_cell_off[z + 1]; ++i)
+  {
+    const int32_t* cn = cell_node + 3 * (size_t)node_cell[i];
+    for (int j = 0; j < 3; ++j)
+      cnt += (cn[j] < z) ? 1 : 0;
+  }
+  pending[z] = cnt;
+  if (cnt == 0)
+    queue[atomicAdd(&ctl[3], 1u)] = z;  // ctl[3]: queue tail
+}
+
+// Variant for meshes whose dependency wavefront fits the device: every thread owns ONE vertex (handed out in index
+// order by a ticket counter, so whatever a thread waits for is resident or finished) and retries until its lower
+// neighbours are decided.  No queue, no counters: 3.7 us per wavefront step instead of ~25 us - but only the
+// resident vertices (148 SMs x 2048 threads) are in flight, which on a row-numbered n x n mesh limits the wavefront
+// to 300 k / n rows: 13 ms at 1024^2, an estimated 0.8 s at 4096^2, where the dataflow kernel takes 50 ms.
 __global__ void __launch_bounds__(256)
-greedy_colour_kernel(int n, const int32_t* __restrict__ node_cell_off, const int32_t* __restrict__ node_cell,
+greedy_colour_ticket_kernel(int n, const int32_t* __restrict__ node_cell_off, const int32_t* __restrict__ node_cell,
                      const int32_t* __restrict__ cell_node, const uint8_t* __restrict__ skip, int* colour, unsigned* ticket,
-                     int* status)
+                     int* status, unsigned* maxcol)
 {
   __shared__ unsigned s_base;
   if (threadIdx.x == 0)
@@ -891,8 +919,11 @@ greedy_colour_kernel(int n, const int32_t* __restrict__ node_cell_off, const int
     pending = still;
     if (!pending)
     {
-      vc[z] = __ffsll((long long)~used) - 1;
+      const int c = __ffsll((long long)~used) - 1;
+      vc[z] = c;
       __threadfence();
+      if ((unsigned)(c + 1) > *(volatile unsigned*)maxcol)
+        atomicMax(maxcol, (unsigned)(c + 1));
       done = true;
     }
     else if (++spins > (1L << 22))
@@ -904,6 +935,78 @@ greedy_colour_kernel(int n, const int32_t* __restrict__ node_cell_off, const int
       __nanosleep(32);
   }
 }
+
+// ctl: [0] queue head, [1] status, [2] max colour + 1, [3] queue tail
+__global__ void __launch_bounds__(256)
+greedy_colour_kernel(int n, const int32_t* __restrict__ node_cell_off, const int32_t* __restrict__ node_cell,
+                     const int32_t* __restrict__ cell_node, const uint8_t* __restrict__ skip, int* colour, int* pending,
+                     int* queue, unsigned* ctl)
+{
+  volatile int* vq = queue;
+  volatile int* vc = colour;
+  volatile unsigned* vctl = ctl;
+  while (true)
+  {
+    const unsigned slot = atomicAdd(&ctl[0], 1u);
+    if (slot >= (unsigned)n)
+      return;
+    // the slot is filled by whoever releases the slot-th ready vertex; all poppers are resident (persistent grid)
+    // (claiming 32 slots per warp only when the queue is non-empty was measured slower: 108 vs 71 ms at 1024^2)
+    int z = vq[slot];
+    long spins = 0;
+    while (z < 0)
+    {
+      if (++spins > (1L << 24))
+      {
+        atomicExch(&ctl[1], 1u);  // no progress: reported by the host, never silent
+        return;
+      }
+      __nanosleep(32);
+      z = vq[slot];
+    }
+    __threadfence();  // the colours published before the release of z are visible
+    const int c0 = node_cell_off[z], c1 = node_cell_off[z + 1];
+    if (!(skip && skip[z]))
+    {
+      unsigned long long used = 0ull;
+      for (int i = c0; i < c1; ++i)
+      {
+        const int32_t* cn = cell_node + 3 * (size_t)node_cell[i];
+        for (int j = 0; j < 3; ++j)
+        {
+          const int w = cn[j];
+          if (w < z)
+          {
+            const int c = vc[w];
+            if (c >= 0)
+              used |= 1ull << c;
+          }
+        }
+      }
+      const int c = __ffsll((long long)~used) - 1;
+      vc[z] = c;
+      if ((unsigned)(c + 1) > vctl[2])
+        atomicMax(&ctl[2], (unsigned)(c + 1));
+    }
+    __threadfence();  // colour before the releases
+    for (int i = c0; i < c1; ++i)
+    {
+      const int32_t* cn = cell_node + 3 * (size_t)node_cell[i];
+      for (int j = 0; j < 3; ++j)
+      {
+        const int u = cn[j];
+        if (u > z && atomicSub(&pending[u], 1) == 1)
+        {
+          // last release of u: the fence orders the colour stores of all earlier releasers (each fenced before its
+          // decrement of the same counter) before the queue entry
+          __threadfence();
+          const unsigned t = atomicAdd(&ctl[3], 1u);
+          vq[t] = u;
+        }
+      }
+    }
+  }
+}
 } // namespace
 
 // Colours of all vertices (-1 for skipped vertices).  Two halves so that the caller can overlap the kernel with
@@ -911,24 +1014,11 @@ greedy_colour_kernel(int n, const int32_t* __restrict__ node_cell_off, const int
 // stream, `finish` fetches the result into the host vector and returns the number of colours.
 struct ColouringJob
 {
-  DevBuf<int> d_col;
-  DevBuf<unsigned> d_ctl;  // [ticket, status, max colour + 1]
+  DevBuf<int> d_col, d_pending, d_queue;
+  DevBuf<unsigned> d_ctl;  // [queue head, status, max colour + 1, queue tail]
   DevBuf<uint8_t> d_skip;
+  bool ticket = false;
 };
-
-namespace
-{
-__global__ void max_colour_kernel(const int* __restrict__ colour, int n, unsigned* out)
-{
-  int m = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    m = max(m, colour[i] + 1);
-  for (int o = 16; o; o >>= 1)
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0)
-    atomicMax(out, (unsigned)m);
-}
-} // namespace
 
 std::shared_ptr<ColouringJob> device_greedy_colouring_start(eqlb_handle* h, const uint8_t* h_skip)
 {
@@ -944,13 +1034,38 @@ std::shared_ptr<ColouringJob> device_greedy_colouring_start(eqlb_handle* h, cons
     job->d_skip.alloc(n);
     CUDA_CHECK(cudaMemcpyAsync(job->d_skip.p, h_skip, n, cudaMemcpyHostToDevice, h->stream));
   }
-  fill_int_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(job->d_col.p, n, -2);
+  const int nb = (n + 255) / 256;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  // ticket kernel while the wavefront of a row-numbered mesh fits the resident threads (~n^1.5 / resident steps),
+  // dataflow kernel beyond; EQLB_COLOURING=ticket|dataflow overrides.  Both give the sequential first-fit colouring.
+  static const char* force = getenv("EQLB_COLOURING");
+  const double steps_ticket = (double)n * std::sqrt((double)n) / ((double)nsm * 2048.0);
+  const bool ticket = force ? (force[0] == 't') : steps_ticket < 1.5e5;  // measured crossover on B200: between 2048^2 (ticket 183 vs 215 ms per eqlb_create) and 3072^2 (437 vs 409 ms)
+  if (ticket)
+  {
+    job->ticket = true;
+    fill_int_kernel<<<nb, 256, 0, h->stream>>>(job->d_col.p, n, -2);
+    greedy_colour_ticket_kernel<<<nb, 256, 0, h->stream>>>(n, h->d_node_cell_off.p, h->d_node_cell.p, h->d_cell_node.p,
+                                                            h_skip ? job->d_skip.p : nullptr, job->d_col.p, job->d_ctl.p,
+                                                            reinterpret_cast<int*>(job->d_ctl.p + 1), job->d_ctl.p + 2);
+    CUDA_CHECK(cudaGetLastError());
+    return job;
+  }
+  job->d_pending.alloc(n);
+  job->d_queue.alloc(n);
+  fill_int_kernel<<<nb, 256, 0, h->stream>>>(job->d_col.p, n, -1);
+  fill_int_kernel<<<nb, 256, 0, h->stream>>>(job->d_queue.p, n, -1);
+  colour_count_kernel<<<nb, 256, 0, h->stream>>>(n, h->d_node_cell_off.p, h->d_node_cell.p, h->d_cell_node.p, job->d_pending.p,
+                                                 job->d_queue.p, job->d_ctl.p);
   CUDA_CHECK(cudaGetLastError());
-  greedy_colour_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_node_cell_off.p, h->d_node_cell.p, h->d_cell_node.p,
-                                                               h_skip ? job->d_skip.p : nullptr, job->d_col.p, job->d_ctl.p,
-                                                               reinterpret_cast<int*>(job->d_ctl.p + 1));
-  CUDA_CHECK(cudaGetLastError());
-  max_colour_kernel<<<296, 256, 0, h->stream>>>(job->d_col.p, n, job->d_ctl.p + 2);
+  // persistent grid: every CTA must be resident (the poppers wait for each other's releases)
+  int per_sm = 1;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_colour_kernel, 256, 0));
+  const int grid = std::max(1, std::min(nb, nsm * std::max(1, std::min(per_sm, 4))));
+  greedy_colour_kernel<<<grid, 256, 0, h->stream>>>(n, h->d_node_cell_off.p, h->d_node_cell.p, h->d_cell_node.p,
+                                                    h_skip ? job->d_skip.p : nullptr, job->d_col.p, job->d_pending.p,
+                                                    job->d_queue.p, job->d_ctl.p);
   CUDA_CHECK(cudaGetLastError());
   return job;
 }
@@ -964,8 +1079,8 @@ int device_greedy_colouring_finish(eqlb_handle* h, ColouringJob& job, std::vecto
   unsigned ctl[4] = {0, 0, 0, 0};
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   CUDA_CHECK(cudaMemcpy(ctl, job.d_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost));
-  eqlb_d2h(colour.data(), job.d_col.p, (size_t)n * sizeof(int));
-  if (ctl[1] != 0)
+  if (ctl[1] != 0 || (!job.ticket && ctl[3] != (unsigned)n))
     throw EqlbError(EQLB_ERR_CUDA, "device colouring made no progress (EQLB_HOST_COLOURING=1 selects the host algorithm)");
+  eqlb_d2h(colour.data(), job.d_col.p, (size_t)n * sizeof(int));
   return (int)ctl[2];
 }

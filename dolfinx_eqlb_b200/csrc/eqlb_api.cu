@@ -17,6 +17,8 @@
 static thread_local std::string g_last_error;
 void eqlb_set_error(const std::string& msg) { g_last_error = msg; }
 
+void ensure_host_topology(eqlb_handle* h);  // host copies of the vertex connectivity, fetched from the device on first use
+
 namespace
 {
 
@@ -68,25 +70,113 @@ struct StageTimer
   }
 };
 
+// (segment, lane class) bookkeeping shared by the host and the device ordering: a lane class with few members
+// joins the next wider one (saves a launch)
+static void merge_small_classes(int32_t* cc, int8_t* cm)
+{
+  cm[0] = 0, cm[1] = 1, cm[2] = 2, cm[3] = 3;
+  const int thr = std::max(8192, (cc[0] + cc[1] + cc[2]) / 16);
+  if (cc[1] > 0 && cc[1] < thr && cc[2] > 0)
+    cm[1] = 2, cc[2] += cc[1], cc[1] = 0;
+  if (cc[0] > 0 && cc[0] < thr && cc[1] + cc[2] > 0)
+  {
+    cm[0] = cc[1] > 0 ? 1 : 2;
+    cc[cm[0]] += cc[0], cc[0] = 0;
+  }
+}
+
+// Launch order computed on the device (patch_builder.cu): raw keys + histogram, the host derives segment offsets,
+// lane-class merging and the launch list from the 4096 counts, a stable radix sort writes h->d_order.
+static void order_on_device(eqlb_handle* h, ColouringJob& job, int ncol, int nchunk, int ngrouped)
+{
+  std::vector<uint32_t> hist;
+  device_order_histogram(h, colouring_job_colours(job), nchunk, hist);
+  h->nseg = nchunk * ncol;
+  h->h_colour_off.assign(h->nseg + 1, 0);
+  h->h_colour_fast.assign(h->nseg, 0);
+  h->h_seg_subs.assign(h->nseg, {});
+  std::vector<uint16_t> rank(4096, 0xFFFF);
+  int32_t at = ngrouped;  // grouped patches occupy the head of the order
+  for (int chunk = 0; chunk < nchunk; ++chunk)
+    for (int col = 0; col < ncol; ++col)
+    {
+      const int sg = chunk * ncol + col;
+      const uint32_t* hh = &hist[(size_t)((chunk * 64 + col) << 2)];
+      int32_t cc[3] = {(int32_t)hh[0], (int32_t)hh[1], (int32_t)hh[2]};
+      int8_t cm[4];
+      merge_small_classes(cc, cm);
+      h->h_colour_off[sg] = at;
+      for (int cl = 0; cl < 4; ++cl)
+      {
+        const int32_t first = at;
+        for (int raw = 0; raw < 4; ++raw)
+          if (cm[raw] == cl)
+          {
+            at += (int32_t)hh[raw];
+            rank[(size_t)(((chunk * 64 + col) << 2) | raw)] = (uint16_t)(sg * 4 + cl);
+          }
+        if (cl < 3 && at > first)
+        {
+          h->h_seg_subs[sg].push_back({first, at - first, 4 << cl, -1});
+          h->h_colour_fast[sg] += at - first;
+        }
+      }
+    }
+  h->h_colour_off[h->nseg] = at;
+  if (at != h->nactive)
+    throw EqlbError(EQLB_ERR_STATE, "device launch order: patch count mismatch");
+  h->h_order.clear();
+  device_order_sort(h, rank, ngrouped, at - ngrouped);
+  h->h_se_slabs.clear();
+  h->h_ev_slabs.clear();
+  h->slabs_pending = nchunk > 1;
+  h->ordered = true;
+}
+
+// result slabs of the host pipeline (a range of DOFs can go back to the host after the last stage with a patch
+// that adds into it), computed on first use when the launch order came from the device
+void ensure_slabs(eqlb_handle* h)
+{
+  if (!h->slabs_pending)
+    return;
+  const int nchunk = h->nchunk;
+  std::vector<int> cfin, ffin;
+  device_slab_stages(h, nchunk, cfin, ffin);
+  auto slab_lo = [&](long cnt, int sidx) { return (size_t)(cnt * sidx / nchunk); };
+  const int kk = h->k;
+  const size_t ncd = (size_t)(kk * kk - kk);
+  h->h_se_slabs.clear();
+  h->h_ev_slabs.clear();
+  for (int sidx = 0; sidx < nchunk; ++sidx)
+  {
+    const size_t c0 = slab_lo(h->ncell, sidx), c1 = slab_lo(h->ncell, sidx + 1);
+    h->h_se_slabs.push_back({c0 * h->nrt, (c1 - c0) * h->nrt, cfin[sidx]});
+    if (ncd)
+      h->h_ev_slabs.push_back({(size_t)h->nfct * kk + c0 * ncd, (c1 - c0) * ncd, cfin[sidx]});
+    const size_t f0 = slab_lo(h->nfct, sidx), f1 = slab_lo(h->nfct, sidx + 1);
+    h->h_ev_slabs.push_back({f0 * kk, (f1 - f0) * kk, ffin[sidx]});
+  }
+  h->slabs_pending = false;
+}
+
 void colour_patches(eqlb_handle* h)
 {
   // topology arrays: the caller's (during eqlb_create) or the handle's copies (stress handles,
   // which may have to recolour when a BC set groups boundary patches)
-  const eqlb_handle::HostTopo& T = h->topo;
-  if (!T.node_cell_off)
-  {
-    if (h->nactive == 0 && h->nseg > 0)
-      return;  // nothing owned: the (empty) colouring of eqlb_create stands
-    throw EqlbError(EQLB_ERR_STATE, "colouring: host topology not available");
-  }
+  if (h->nactive == 0 && h->nseg > 0)
+    return;  // nothing owned: the (empty) colouring of eqlb_create stands
   const int n = h->nnode;
   int ncol = 0;
   const auto t_enter = std::chrono::steady_clock::now();
   const int ngrouped = h->h_group_off.empty() ? 0 : h->h_group_off.back();
   static const bool host_col = getenv("EQLB_HOST_COLOURING") && atoi(getenv("EQLB_HOST_COLOURING")) != 0;
+  std::shared_ptr<ColouringJob> job;
   if (host_col || !h->d_node_cell.p || !h->d_cell_node.p)
   {
     // sequential first-fit colouring on the host (reference implementation of the device kernel)
+    if (!h->topo.node_cell_off)
+      ensure_host_topology(h);
+    const eqlb_handle::HostTopo& T = h->topo;
     h->h_colour.assign(n, -1);
     for (int z = 0; z < n; ++z)
     {
@@ -114,7 +204,7 @@ void colour_patches(eqlb_handle* h)
   {
     // the same colouring, computed on the device from the uploaded connectivity (patch_builder.cu); eqlb_create
     // has queued the kernel already (h->colouring_job) and uploaded the rest of the mesh meanwhile
-    std::shared_ptr<ColouringJob> job = h->colouring_job;
+    job = h->colouring_job;
     h->colouring_job.reset();
     if (!job)
     {
@@ -161,6 +251,16 @@ void colour_patches(eqlb_handle* h)
     nchunk = 2;
   }
   h->nchunk = nchunk;
+  static const bool host_order = getenv("EQLB_HOST_ORDER") && atoi(getenv("EQLB_HOST_ORDER")) != 0;
+  if (job && !h->interface_first && nchunk <= 16 && !host_order)
+  {
+    order_on_device(h, *job, ncol, nchunk, ngrouped);
+    ctm.lap("  colouring: launch order (device)");
+    return;
+  }
+  if (!h->topo.node_cell_off)
+    ensure_host_topology(h);
+  const eqlb_handle::HostTopo& T = h->topo;
   // stage of a patch = chunk of its LAST cell: all its inputs are on the device once the
   // cell slabs 0..stage have arrived
   auto chunk_of = [&](int z)
@@ -364,6 +464,9 @@ void colour_patches(eqlb_handle* h)
     }
     ctm.lap("  colouring: result slabs");
   }
+  h->d_order.upload(h->h_order.data(), h->h_order.size());
+  h->slabs_pending = false;
+  h->ordered = true;
 }
 
 void append(std::vector<double>& dst, const double* src, size_t n, int& offset)
@@ -393,7 +496,7 @@ eqlb_handle::~eqlb_handle()
 // Host copies of the connectivity around the vertices (grouping of boundary patches, re-colouring after a BC set
 // has grouped patches): fetched from the device on first use - most handles never need them (the caller's arrays
 // are not referenced after eqlb_create).
-static void ensure_host_topology(eqlb_handle* h)
+void ensure_host_topology(eqlb_handle* h)
 {
   if (!h->h_node_cell_off.empty())
     return;
@@ -477,24 +580,19 @@ static void finish_bcs(eqlb_handle* h, const int8_t* facet_type, const int8_t* n
           h->h_group_off.push_back((int32_t)gorder.size());
         }
       }
-      if (!gorder.empty() || h->h_order.empty() || h->coloured_with_groups)
-      {
-        ensure_host_topology(h);
+      if (!gorder.empty() || !h->ordered || h->coloured_with_groups)
         colour_patches(h);
-      }
       h->coloured_with_groups = !gorder.empty();
-      std::copy(gorder.begin(), gorder.end(), h->h_order.begin());
+      if (!gorder.empty())
+        CUDA_CHECK(cudaMemcpy(h->d_order.p, gorder.data(), gorder.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     else
     {
       // the colouring of eqlb_create is still valid unless a previous BC set grouped patches
       h->h_grouped.assign(h->nnode, 0);
       h->h_group_off.clear();
-      if (h->coloured_with_groups || h->h_order.empty())
-      {
-        ensure_host_topology(h);
+      if (h->coloured_with_groups || !h->ordered)
         colour_patches(h);
-      }
       h->coloured_with_groups = false;
     }
 
@@ -658,6 +756,7 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
         h->d_cell_node.upload(mesh->cell_node, nc * 3);
         h->d_node_cell_off.upload(mesh->node_cell_off, nn + 1);
         h->d_node_cell.upload(mesh->node_cell, mesh->node_cell_off[nn]);
+        h->d_node_fct_off.upload(mesh->node_fct_off, nn + 1);  // (lane classes of the device launch order)
         static const bool host_col = getenv("EQLB_HOST_COLOURING") && atoi(getenv("EQLB_HOST_COLOURING")) != 0;
         std::vector<uint8_t> skip;
         if (!host_col)
@@ -685,7 +784,6 @@ int eqlb_create(const eqlb_mesh* mesh, const eqlb_tables* t, int nrhs, uint32_t 
                 hp->d_fct_node.upload(mesh->fct_node, nf * 2);
                 hp->d_fct_cell_off.upload(mesh->fct_cell_off, nf + 1);
                 hp->d_fct_cell.upload(mesh->fct_cell, mesh->fct_cell_off[nf]);
-                hp->d_node_fct_off.upload(mesh->node_fct_off, nn + 1);
                 hp->d_node_fct.upload(mesh->node_fct, mesh->node_fct_off[nn]);
                 hp->d_fct_perms.upload(mesh->fct_perms, nc * 3);
               }
@@ -1337,6 +1435,7 @@ static void run_equilibration(eqlb_handle* h, bool ev, const double* const* G, c
   }
 
   // ---- staged: copy-in stream, compute stream (the caller's), copy-out stream ----
+  ensure_slabs(h);
   const int nst = h->nchunk;
   if (!h->s_h2d)
   {

@@ -252,6 +252,10 @@ struct eqlb_handle
     int64_t recoff;               // offset of its lane records in d_prec
   };
   std::shared_ptr<ColouringJob> colouring_job;  // queued by eqlb_create, consumed by colour_patches
+  DevBuf<int32_t> d_order;      // [nactive] patches in launch order (grouped patches first)
+  DevBuf<uint16_t> d_rawkey;    // [nnode] ((chunk*64 + colour) << 2 | lane class) of the device launch order, 0xFFFF = not launched
+  bool ordered = false;         // colouring + launch order are valid
+  bool slabs_pending = false;   // result slabs of the host pipeline still to be computed from d_rawkey (ensure_slabs)
   std::vector<std::vector<FastSub>> h_seg_subs;  // [nseg] (empty: no lane-per-cell launch)
   int nsub = 0;
   DevBuf<int64_t> d_seginfo;            // [nsub][4] first, count, lanes, recoff
@@ -283,6 +287,10 @@ struct eqlb_handle
 void launch_compute_cellJ(eqlb_handle* h);
 // exact sequential first-fit colouring, computed on the device (patch_builder.cu)
 struct ColouringJob;
+const int* colouring_job_colours(const ColouringJob& job);  // device colours of a job
+void device_order_histogram(eqlb_handle* h, const int* d_colour, int nchunk, std::vector<uint32_t>& hist);
+void device_order_sort(eqlb_handle* h, const std::vector<uint16_t>& rank, int offset, int count);
+void device_slab_stages(eqlb_handle* h, int nchunk, std::vector<int>& cfin, std::vector<int>& ffin);
 std::shared_ptr<ColouringJob> device_greedy_colouring_start(eqlb_handle* h, const uint8_t* h_skip);
 int device_greedy_colouring_finish(eqlb_handle* h, ColouringJob& job, std::vector<int32_t>& colour);
 void launch_patch_builder(eqlb_handle* h, int32_t* d_ncells_out, int32_t* d_cells, int32_t* d_fcts, int8_t* d_inodes,

@@ -14,6 +14,8 @@
 // eqlb_set_bcs, not per equilibration.
 #include <cmath>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "eqlb_internal.cuh"
 
 namespace
@@ -762,13 +764,13 @@ void launch_patch_builder(eqlb_handle* h, int32_t* x_ncells, int32_t* x_cells, i
                           int8_t* x_fl, int8_t* x_type, uint8_t* x_rev, uint8_t* x_reversion)
 {
   const bool expand = x_ncells || x_cells || x_fcts || x_inod || x_fl || x_type || x_rev || x_reversion;
-  DevBuf<int32_t> d_order;
-  d_order.upload(h->h_order.data(), h->h_order.size());
   const int bs = 128;
   if (h->nactive == 0)
     return;
+  if (h->d_order.n < (size_t)h->nactive)
+    throw EqlbError(EQLB_ERR_STATE, "patch builder: launch order not available");
   patch_builder_kernel<<<(h->nactive + bs - 1) / bs, bs, 0, h->stream>>>(
-      h->mesh_view(), h->d_facet_type.p, h->nrhs, d_order.p, h->nactive, h->pstride, h->ncmax,
+      h->mesh_view(), h->d_facet_type.p, h->nrhs, h->d_order.p, h->nactive, h->pstride, h->ncmax,
       expand ? nullptr : h->d_pnode.p, h->d_pncells.p, expand ? nullptr : h->d_pcell.p, h->d_pinfo.p,
       expand ? nullptr : h->d_prhs.p, expand ? nullptr : h->d_prec.p, h->d_seginfo.p, h->nsub, x_ncells, x_cells, x_fcts, x_inod, x_fl, x_type, x_rev, x_reversion);
   CUDA_CHECK(cudaGetLastError());
@@ -1070,6 +1072,8 @@ std::shared_ptr<ColouringJob> device_greedy_colouring_start(eqlb_handle* h, cons
   return job;
 }
 
+const int* colouring_job_colours(const ColouringJob& job) { return job.d_col.p; }
+
 int device_greedy_colouring_finish(eqlb_handle* h, ColouringJob& job, std::vector<int32_t>& colour)
 {
   const int n = h->nnode;
@@ -1083,4 +1087,183 @@ int device_greedy_colouring_finish(eqlb_handle* h, ColouringJob& job, std::vecto
     throw EqlbError(EQLB_ERR_CUDA, "device colouring made no progress (EQLB_HOST_COLOURING=1 selects the host algorithm)");
   eqlb_d2h(colour.data(), job.d_col.p, (size_t)n * sizeof(int));
   return (int)ctl[2];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Launch order on the device: counting sort of the active patches by (segment, lane class), vertex order
+// within a class (stable radix sort), and the result slabs of the host pipeline.  Raw key of a patch:
+// ((chunk * 64 + colour) << 2) | lane class  (< 4096: at most 16 chunks, 64 colours), 0xFFFF for patches that
+// are not launched (not owned / grouped).  The host turns the 4096-bin histogram into segment offsets, merges
+// small lane classes and sends back the rank of every raw key in launch order.
+// ---------------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int ORDER_BINS = 4096;
+
+__global__ void __launch_bounds__(256)
+order_rawkey_kernel(int n, const int32_t* __restrict__ node_cell_off, const int32_t* __restrict__ node_cell,
+                    const int32_t* __restrict__ node_fct_off, const int* __restrict__ colour, int nchunk, int ncell, int nrhs,
+                    uint16_t* __restrict__ rawkey, unsigned* __restrict__ hist)
+{
+  __shared__ unsigned s_hist[ORDER_BINS];
+  for (int i = threadIdx.x; i < ORDER_BINS; i += blockDim.x)
+    s_hist[i] = 0u;
+  __syncthreads();
+  const long per = ((long)n + gridDim.x - 1) / gridDim.x;
+  const long z0 = per * blockIdx.x, z1 = min((long)n, z0 + per);
+  for (long z = z0 + threadIdx.x; z < z1; z += blockDim.x)
+  {
+    const int col = colour[z];
+    unsigned key = 0xFFFFu;
+    if (col >= 0)
+    {
+      const int c0 = node_cell_off[z], c1 = node_cell_off[z + 1];
+      int cmax = 0;
+      for (int i = c0; i < c1; ++i)
+        cmax = max(cmax, node_cell[i]);
+      const int chunk = (int)((long)cmax * nchunk / max(ncell, 1));
+      const int nf = node_fct_off[z + 1] - node_fct_off[z], nc = c1 - c0;
+      const int cls = (nf > 16 || !(nrhs == 1 || nf == nc)) ? 3 : (nf <= 4 ? 0 : (nf <= 8 ? 1 : 2));
+      key = (unsigned)(((chunk * 64 + col) << 2) | cls);
+      atomicAdd(&s_hist[key], 1u);
+    }
+    rawkey[z] = (uint16_t)key;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ORDER_BINS; i += blockDim.x)
+    if (s_hist[i])
+      atomicAdd(&hist[i], s_hist[i]);
+}
+
+__global__ void order_sortkey_kernel(int n, const uint16_t* __restrict__ rawkey, const uint16_t* __restrict__ rank,
+                                     uint16_t* __restrict__ sortkey, int32_t* __restrict__ iota)
+{
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= n)
+    return;
+  const uint16_t r = rawkey[z];
+  sortkey[z] = (r == 0xFFFFu) ? (uint16_t)0xFFFFu : rank[r];
+  iota[z] = z;
+}
+
+// last stage that adds into the cells / facets of every result slab (slab s of `cnt` items: [cnt s / nchunk, cnt (s+1) / nchunk))
+__global__ void __launch_bounds__(256)
+slab_stage_kernel(int ncell, int nfct, const int32_t* __restrict__ cell_node, const int32_t* __restrict__ fct_node,
+                  const uint16_t* __restrict__ rawkey, int nchunk, int* __restrict__ cfin, int* __restrict__ ffin)
+{
+  __shared__ int s_c[16], s_f[16];
+  if (threadIdx.x < 16)
+    s_c[threadIdx.x] = s_f[threadIdx.x] = 0;
+  __syncthreads();
+  auto stage = [&](int v)
+  {
+    const unsigned r = rawkey[v];
+    return r == 0xFFFFu ? -1 : (int)(r >> 8);
+  };
+  auto slab = [&](long i, long cnt)
+  {
+    int s0 = (int)(i * nchunk / max(cnt, 1L));
+    while (s0 + 1 < nchunk && cnt * (s0 + 1) / nchunk <= i)
+      ++s0;
+    while (s0 > 0 && cnt * s0 / nchunk > i)
+      --s0;
+    return s0;
+  };
+  const long stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long c = t0; c < ncell; c += stride)
+  {
+    const int st = max(stage(cell_node[3 * c]), max(stage(cell_node[3 * c + 1]), stage(cell_node[3 * c + 2])));
+    if (st > 0)
+      atomicMax(&s_c[slab(c, ncell)], st);
+  }
+  for (long f = t0; f < nfct; f += stride)
+  {
+    const int st = max(stage(fct_node[2 * f]), stage(fct_node[2 * f + 1]));
+    if (st > 0)
+      atomicMax(&s_f[slab(f, nfct)], st);
+  }
+  __syncthreads();
+  if (threadIdx.x < nchunk)
+  {
+    if (s_c[threadIdx.x] > 0)
+      atomicMax(&cfin[threadIdx.x], s_c[threadIdx.x]);
+    if (s_f[threadIdx.x] > 0)
+      atomicMax(&ffin[threadIdx.x], s_f[threadIdx.x]);
+  }
+}
+} // namespace
+
+// step 1: raw keys + histogram (host vector of ORDER_BINS counts); the raw keys stay in h->d_rawkey
+void device_order_histogram(eqlb_handle* h, const int* d_colour, int nchunk, std::vector<uint32_t>& hist)
+{
+  const int n = h->nnode;
+  hist.assign(ORDER_BINS, 0u);
+  if (n == 0)
+    return;
+  if (nchunk > 16)
+    throw EqlbError(EQLB_ERR_STATE, "device launch order: more than 16 chunks");
+  h->d_rawkey.alloc(n);
+  DevBuf<unsigned> d_hist;
+  d_hist.alloc(ORDER_BINS);
+  d_hist.zero(h->stream);
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  const int grid = std::max(1, std::min((n + 255) / 256, nsm * 4));
+  order_rawkey_kernel<<<grid, 256, 0, h->stream>>>(n, h->d_node_cell_off.p, h->d_node_cell.p, h->d_node_fct_off.p, d_colour, nchunk,
+                                                   h->ncell, h->nrhs, h->d_rawkey.p, d_hist.p);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(hist.data(), d_hist.p, ORDER_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+// step 2: rank[raw key] = position of its (segment, merged class) in launch order -> h->d_order[offset ...)
+void device_order_sort(eqlb_handle* h, const std::vector<uint16_t>& rank, int offset, int count)
+{
+  const int n = h->nnode;
+  h->d_order.alloc((size_t)std::max(h->nactive, 1));
+  if (n == 0 || count == 0)
+    return;
+  DevBuf<uint16_t> d_rank, d_key_in, d_key_out;
+  DevBuf<int32_t> d_val_in, d_val_out;
+  d_rank.alloc(ORDER_BINS);
+  CUDA_CHECK(cudaMemcpyAsync(d_rank.p, rank.data(), ORDER_BINS * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+  d_key_in.alloc(n);
+  d_key_out.alloc(n);
+  d_val_in.alloc(n);
+  d_val_out.alloc(n);
+  order_sortkey_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_rawkey.p, d_rank.p, d_key_in.p, d_val_in.p);
+  CUDA_CHECK(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key_in.p, d_key_out.p, d_val_in.p, d_val_out.p, n, 0, 16, h->stream));
+  DevBuf<uint8_t> d_tmp;
+  d_tmp.alloc(std::max<size_t>(tmp_bytes, 1));
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_key_in.p, d_key_out.p, d_val_in.p, d_val_out.p, n, 0, 16, h->stream));
+  // the launched patches come first (skipped ones carry the key 0xFFFF)
+  CUDA_CHECK(cudaMemcpyAsync(h->d_order.p + offset, d_val_out.p, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+// result slabs of the host pipeline from the raw keys (needs the facet connectivity on the device)
+void device_slab_stages(eqlb_handle* h, int nchunk, std::vector<int>& cfin, std::vector<int>& ffin)
+{
+  cfin.assign(nchunk, 0);
+  ffin.assign(nchunk, 0);
+  if (h->nnode == 0 || nchunk > 16)
+    return;
+  DevBuf<int> d_fin;
+  d_fin.alloc(32);
+  d_fin.zero(h->stream);
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  slab_stage_kernel<<<nsm * 4, 256, 0, h->stream>>>(h->ncell, h->nfct, h->d_cell_node.p, h->d_fct_node.p, h->d_rawkey.p, nchunk,
+                                                   d_fin.p, d_fin.p + 16);
+  CUDA_CHECK(cudaGetLastError());
+  int fin[32];
+  CUDA_CHECK(cudaMemcpyAsync(fin, d_fin.p, sizeof(fin), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int s2 = 0; s2 < nchunk; ++s2)
+  {
+    cfin[s2] = fin[s2];
+    ffin[s2] = fin[16 + s2];
+  }
 }

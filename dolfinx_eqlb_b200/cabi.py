@@ -190,6 +190,8 @@ def load_library():
     lib.eqlb_halo_apply.restype = C.c_int
     lib.eqlb_halo_status.argtypes = [H, C.c_void_p]
     lib.eqlb_halo_status.restype = C.c_int
+    lib.eqlb_get_launch_order.argtypes = [C.c_void_p, c_int32_p, C.POINTER(C.c_int32), c_int32_p]
+    lib.eqlb_get_launch_order.restype = C.c_int
     lib.eqlb_get_staged_flux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.eqlb_get_staged_flux.restype = C.c_int
     lib.eqlb_halo_destroy.argtypes = [H]

@@ -1301,6 +1301,23 @@ int eqlb_set_part(eqlb_handle* h, int part)
       });
 }
 
+int eqlb_get_launch_order(eqlb_handle* h, int32_t* order, int32_t* nchunk, int32_t* seg_off)
+{
+  return guarded(
+      [&]
+      {
+        if (!h || !h->bcs_set)
+          throw EqlbError(EQLB_ERR_STATE, "eqlb_get_launch_order: boundary conditions not set");
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (order && h->nactive > 0)
+          CUDA_CHECK(cudaMemcpy(order, h->d_order.p, (size_t)h->nactive * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (nchunk)
+          *nchunk = h->nchunk;
+        if (seg_off)
+          std::memcpy(seg_off, h->h_colour_off.data(), h->h_colour_off.size() * sizeof(int32_t));
+      });
+}
+
 int eqlb_get_staged_flux(eqlb_handle* h, int r, int is_ev, double** device_ptr, int64_t* n)
 {
   return guarded(

@@ -284,6 +284,12 @@ int eqlb_halo_apply(eqlb_halo* h, double* const* x, int nrhs, void* cuda_stream)
  * never arrives costs seconds, not a hung GPU) */
 int eqlb_halo_status(eqlb_halo* h, void* cuda_stream);
 
+/* Launch order of the patches (inspection / tests): order [number of owned nodes] = node ids sorted by
+ * (segment = chunk * ncolours + colour, lane class, node id), grouped boundary patches first; nchunk = spatial
+ * chunks (stages of the host pipeline); seg_off [nchunk*ncolours + 1] = offsets of the segments in `order`.
+ * The reference has no counterpart (it loops over the nodes in index order, `se/reconstruction.hpp:150-160`). */
+int eqlb_get_launch_order(eqlb_handle* h, int32_t* order, int32_t* nchunk, int32_t* seg_off);
+
 /* Device copy of the flux vector r written by the last host-buffer call (EQLB_HOST / EQLB_HOST_ZEROED) of this
  * handle: distributed callers run the halo sum on it (eqlb_halo_apply) and fetch only the shared DOFs again,
  * instead of holding back the whole copy-out until the exchange is done (dolfinx_eqlb_b200/dist.py

@@ -278,3 +278,51 @@ def test_permuted_dg_dofmap(k):
             assert np.abs(eq.list_flux[0] - ref[cls]).max() < 1e-11 * np.abs(ref[cls]).max()
     finally:
         del m.dg_dofmap
+
+
+@pytest.mark.parametrize("kind,n,scramble,pipeline", [("randdiag", 40, 2, False), ("crossed", 40, 3, True), ("fan", 8, 1, False)])
+def test_device_launch_order(kind, n, scramble, pipeline):
+    """The launch order computed on the device (raw keys + histogram + stable radix sort) is the order the rule
+    defines: patches sorted by (segment = chunk * ncolours + colour, lane class with small classes merged into the
+    next wider one, node id); chunk of a patch = chunk of its last cell (stages of the host pipeline)."""
+    import ctypes as C
+
+    from common import make_mesh
+    from dolfinx_eqlb_b200 import cabi, tables as tb
+
+    m = make_mesh(kind, n, scramble)
+    T = tb.make_tables(2)
+    eq = eqlb.FluxEqlbEV(2, m, [np.zeros(m.ncell * T.ndg)], [np.zeros(m.ncell * T.ndg * 2)], host_pipeline=pipeline)
+    eq.set_boundary_conditions([m.bfct.astype(np.int32)], [[]])
+    got = eq.problem.patch_maps()
+    colour, ncol = got["colour"], got["ncolours"]
+    order = np.zeros(m.nnode, np.int32)
+    nchunk = C.c_int32()
+    seg_off = np.zeros(64 * 16 + 1, np.int32)
+    lib = eq.problem.lib
+    assert lib.eqlb_get_launch_order(eq.problem.h, order.ctypes.data_as(cabi.c_int32_p), C.byref(nchunk),
+                                     seg_off.ctypes.data_as(cabi.c_int32_p)) == 0
+    nchunk = nchunk.value
+    assert nchunk == (4 if pipeline else 1)
+    ncells = np.diff(m.node_cell_off)
+    nf = np.diff(m.node_fct_off)
+    last_cell = np.array([m.node_cell[m.node_cell_off[z]:m.node_cell_off[z + 1]].max() for z in range(m.nnode)])
+    seg = (last_cell.astype(np.int64) * nchunk // m.ncell) * ncol + colour
+    cls = np.where(nf > 16, 3, np.where(nf <= 4, 0, np.where(nf <= 8, 1, 2)))  # single RHS: every patch is eligible
+    merged = cls.copy()
+    for s_ in range(nchunk * ncol):
+        sel = seg == s_
+        cc = [int((sel & (cls == c)).sum()) for c in range(3)]
+        thr = max(8192, sum(cc) // 16)
+        cm = [0, 1, 2]
+        if 0 < cc[1] < thr and cc[2] > 0:
+            cm[1] = 2
+            cc[2] += cc[1]
+            cc[1] = 0
+        if 0 < cc[0] < thr and cc[1] + cc[2] > 0:
+            cm[0] = 1 if cc[1] > 0 else 2
+        for c in range(3):
+            merged[sel & (cls == c)] = cm[c]
+    want = np.lexsort((np.arange(m.nnode), merged, seg))
+    assert np.array_equal(order, want)
+    assert np.array_equal(seg_off[: nchunk * ncol + 1], np.concatenate([[0], np.cumsum(np.bincount(seg, minlength=nchunk * ncol))]))

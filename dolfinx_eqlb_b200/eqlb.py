@@ -392,10 +392,16 @@ class FluxEquilibrator:
         """Page-lock large host vectors once (`eqlb_pin_host`) so that the host-pointer calls copy
         at PCIe speed; small vectors are not worth the registration cost."""
         lib = cabi.load_library()
-        for a in arrays:
-            if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.nbytes >= min_bytes:
-                if lib.eqlb_pin_host(a.ctypes.data, a.nbytes) == 0:
-                    self._pinned.append(a)
+        todo = [a for a in arrays
+                if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.nbytes >= min_bytes]
+        if not todo:
+            return
+        # the registrations of different vectors run side by side (ctypes releases the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(4, len(todo))) as ex:
+            rcs = list(ex.map(lambda a: lib.eqlb_pin_host(a.ctypes.data, a.nbytes), todo))
+        self._pinned.extend(a for a, rc in zip(todo, rcs) if rc == 0)
 
     def _note_call(self):
         """The first call on a new problem runs from pageable memory (the library stages the copies through its

@@ -290,6 +290,38 @@ def fan_unit_square(nper: int, hub_on_boundary: bool = False, scramble_seed: int
     return build_topology(x, tris.astype(np.int32))
 
 
+def delaunay_unit_square(nb: int, seed: int = 0, scramble_seed: int | None = None) -> Mesh:
+    """Unstructured triangulation of the unit square (stand-in for the reference's gmsh fixture
+    `python/test/unit/utils.py:98-137`): `nb` equal segments per side, jittered interior points at roughly the
+    same spacing, Delaunay triangulation (scipy).  Vertex valences 3..9; every corner gets an interior point on its
+    diagonal so that the corner patch has two cells (a 1-cell patch throws in the reference, `se/Patch.cpp:353-359`)."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    h = 1.0 / nb
+    t = np.arange(nb) * h
+    frame = np.concatenate([np.stack([t, 0 * t], 1), np.stack([1 + 0 * t, t], 1), np.stack([1 - t, 1 + 0 * t], 1),
+                            np.stack([0 * t, 1 - t], 1)])
+    gi, gj = np.meshgrid(np.arange(1, nb), np.arange(1, nb), indexing="xy")
+    inner = np.stack([gi.ravel() * h, gj.ravel() * h], 1) + 0.3 * h * (rng.random(((nb - 1) ** 2, 2)) - 0.5)
+    d = 0.38 * h
+    corners = np.array([[d, d], [1 - d, d], [1 - d, 1 - d], [d, 1 - d]])
+    # the grid points next to the corners would compete with the corner points: drop them
+    keep = ~(((gi.ravel() == 1) | (gi.ravel() == nb - 1)) & ((gj.ravel() == 1) | (gj.ravel() == nb - 1)))
+    x = np.concatenate([frame, inner[keep], corners])
+    tri = Delaunay(x).simplices.astype(np.int32)
+    # drop degenerate slivers on the frame (collinear boundary points)
+    a, b, c = x[tri[:, 0]], x[tri[:, 1]], x[tri[:, 2]]
+    area = 0.5 * np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
+    tri = np.sort(tri[area > 1e-12], axis=1)
+    if scramble_seed is not None:
+        tri = _scramble(tri, np.random.default_rng(scramble_seed))
+    m = build_topology(x, tri)
+    if np.diff(m.node_cell_off).min() < 2:
+        raise RuntimeError("delaunay_unit_square: a vertex with fewer than two cells (try another seed)")
+    return m
+
+
 def submesh(mesh: Mesh, cells: np.ndarray):
     """Sub-mesh of the given cells with an ORDER-PRESERVING renumbering of vertices (and hence of facets and of
     the adjacency lists): a vertex whose whole patch lies in the sub-mesh sees exactly the patch it has in

@@ -15,6 +15,8 @@ def make_mesh(kind, n, scramble=None, perturb=0.0):
         return ms.fan_unit_square(n, False, scramble_seed=scramble)
     if kind == "halffan":  # boundary hub with 3 n cells
         return ms.fan_unit_square(n, True, scramble_seed=scramble)
+    if kind == "delaunay":  # unstructured, n segments per side
+        return ms.delaunay_unit_square(n, seed=5, scramble_seed=scramble)
     raise ValueError(kind)
 
 

@@ -104,3 +104,48 @@ def test_se_lower_degree_data_vs_reference(k, p):
     eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
     eq.equilibrate_fluxes()
     assert rel_err(eq.list_flux[0], ref[0]) < RTOL
+
+
+@pytest.mark.parametrize("n,scramble", [(6, 3), (16, None), (24, 2)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_unstructured_mesh_vs_reference(n, scramble, k):
+    """Delaunay triangulations (valences 2..9 mixed in every colour -> several lane classes per colour, generic
+    kernel for the multi-RHS boundary patches): SE maps + fluxes (3 RHS with different BC sets), EV flux, stress +
+    Korn constants (pure Dirichlet and one traction side) against the reference's own code"""
+    from oracle import pyoracle as po
+    from test_gpu_stress import elasticity_case
+
+    m = make_mesh("delaunay", n, scramble)
+    case = PoissonCase(m, k, [[1, 4], [2], []], seed=5, galerkin=False)
+    bc = case.oracle_bc()
+    ref_maps = pr.se_patch_maps(m, case.T, bc)
+    ref = pr.se_run(m, case.T, bc, case.G, case.F)
+    eq = eqlb.FluxEqlbSE(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    got = eq.problem.patch_maps()
+    for key in INT_KEYS:
+        assert np.array_equal(got[key], ref_maps[key]), key
+    eq.equilibrate_fluxes()
+    for r in range(case.nrhs):
+        assert rel_err(eq.list_flux[r], ref[r]) < RTOL
+    case = PoissonCase(m, k, [[1, 4]], seed=1, hom=True, galerkin=False)
+    ref = pr.ev_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    ev = eqlb.FluxEqlbEV(k, m, case.F, case.G)
+    ev.set_boundary_conditions(case.list_bfct_prime, case.list_bcs)
+    ev.equilibrate_fluxes()
+    assert rel_err(ev.list_flux[0], ref[0]) < RTOL
+    if k >= 2:
+        for nsides in ([], [3]):
+            T, G, f, bfp, bcs, neu = elasticity_case(m, k, nsides, seed=3, galerkin=False)
+            bd = eqlb.boundarydata(bcs, m, T, bfp, True)
+            bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
+            try:
+                sref, kref = pr.se_run(m, T, bc, G, f, stress=True, korn=True)
+            except RuntimeError:
+                continue  # a layout the reference itself refuses on this mesh (2-cell traction patches)
+            es = eqlb.FluxEqlbSE(k, m, f, G, equilibrate_stress=True, estimate_korn_constant=True)
+            es.set_boundary_conditions(bfp, bcs)
+            es.equilibrate_fluxes()
+            for r in range(2):
+                assert rel_err(es.list_flux[r], sref[r]) < RTOL
+            assert rel_err(es.get_korn_constants(), np.sqrt(kref)) < 1e-12

@@ -171,3 +171,36 @@ def test_oracle_matches_reference_ev(kind, n, scramble, hom, k, nsets):
         s = fm.conforming_to_drt(m, case.T, b[r])
         z = np.zeros_like(case.G[r])
         assert fm.check_jump(m, case.T, s, z) < 1e-11
+
+
+@needs_ref
+@pytest.mark.parametrize("n,scramble", [(6, 3), (10, None)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_oracle_matches_reference_on_unstructured_mesh(n, scramble, k):
+    """Delaunay triangulation (stand-in for the reference's gmsh fixture `python/test/unit/utils.py:98-137`): vertex
+    valences 2..9, reversed facets: SE maps bit-exact, SE / EV / stress DOFs <= 1e-11 against the reference"""
+    from oracle import pyoracle as po
+    from test_gpu_stress import elasticity_case
+
+    m = make_mesh("delaunay", n, scramble)
+    case = PoissonCase(m, k, [[1, 4], [2], []], seed=5, galerkin=False)
+    bc = case.oracle_bc()
+    a, b = po.se_patch_maps(m, case.T, bc), pr.se_patch_maps(m, case.T, bc)
+    for key in a:
+        if key != "ncmax":
+            assert np.array_equal(a[key], b[key]), key
+    for x, y in zip(po.se_run(m, case.T, bc, case.G, case.F), pr.se_run(m, case.T, bc, case.G, case.F)):
+        assert np.abs(x - y).max() < 1e-11 * np.abs(y).max()
+    case = PoissonCase(m, k, [[1, 4], []], seed=1, hom=True, galerkin=False)
+    bc = case.oracle_bc()
+    for x, y in zip(po.ev_run(m, case.T, bc, case.G, case.F), pr.ev_run(m, case.T, bc, case.G, case.F)):
+        assert np.abs(x - y).max() < 1e-10 * np.abs(y).max()
+    if k >= 2:
+        T, G, f, bfp, bcs, neu = elasticity_case(m, k, [], seed=3, galerkin=False)
+        bd = eqlb.boundarydata(bcs, m, T, bfp, True)
+        bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
+        so, ko = po.se_run(m, T, bc, G, f, stress=True, korn=True)
+        sr, kr = pr.se_run(m, T, bc, G, f, stress=True, korn=True)
+        for x, y in zip(so, sr):
+            assert np.abs(x - y).max() < 1e-11 * np.abs(y).max()
+        assert np.abs(ko - kr).max() < 1e-13 * np.abs(kr).max()

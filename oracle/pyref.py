@@ -247,3 +247,20 @@ def boundary_data(mesh, tables, list_bcs, list_bfct_prime, stress=False, qdegree
     )
     _check(rc)
     return ft, bv, (nob if stress else None)
+
+
+def local_solver(mesh, tables, qvals, solver="cholesky"):
+    """The reference's `base::local_solver_{lu,cholesky,cg}` (`base/local_solver.hpp`) on the fixed projection forms
+    of `lsolver/projection.py:17-77`: a = (u, v) on DG_p, l_i = (data_i, v), data_i at the cell quadrature points
+    (`qvals[i][cell*nq + q]`).  Returns the DG_p coefficient vectors."""
+    from dolfinx_eqlb_b200.cabi import EqlbTables, PackedTables
+
+    pm, pt = PackedMesh(mesh, tables.ndg), PackedTables(tables)
+    L = lib()
+    L.ref_local_solver.restype = C.c_int
+    L.ref_local_solver.argtypes = [C.POINTER(EqlbMesh), C.POINTER(EqlbTables), C.c_int, C.c_int, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+    qv = [np.ascontiguousarray(q, dtype=np.float64) for q in qvals]
+    out = [np.zeros(mesh.ncell * tables.ndg) for _ in qv]
+    _check(L.ref_local_solver(C.byref(pm.struct), C.byref(pt.struct), len(qv), {"lu": 0, "cholesky": 1, "cg": 2}[solver],
+                              ptr_array(qv), ptr_array(out)))
+    return out

@@ -11,6 +11,7 @@
 #include <dolfinx_eqlb/base/BoundaryData.hpp>
 #include <dolfinx_eqlb/base/FluxBC.hpp>
 #include <dolfinx_eqlb/ev/Patch.hpp>
+#include <dolfinx_eqlb/base/local_solver.hpp>
 #include <dolfinx_eqlb/ev/reconstruction.hpp>
 #include <dolfinx_eqlb/se/reconstruction.hpp>
 
@@ -959,6 +960,76 @@ int ref_boundary_data(const eqlb_mesh* mesh, const ref_element* elmt, int nrhs, 
           for (int i = 0; i < mesh->nnode; ++i)
             node_on_bnd[i] = nb[i];
         }
+      });
+}
+}
+
+extern "C"
+{
+/// The reference's cell-wise solver `base::local_solver_{lu,cholesky,cg}` (`base/local_solver.hpp:38-240`, the
+/// engine of `lsolver/projection.py:17-77`) on the fixed projection forms: a = (u, v) on DG_p, l_i = (data_i, v)
+/// with data_i given at the cell quadrature points, qvals[i] [ncell][nq].  The element loop, the solver and the
+/// scatter are the reference's; the two FFCx cell kernels are restated with the tables of the C ABI (`qwts`, `dg_q`).
+/// solver: 0 = PartialPivLU, 1 = LLT, 2 = ConjugateGradient.  out[i] [ncell*ndg] (DOLFINx DG layout).
+int ref_local_solver(const eqlb_mesh* mesh, const eqlb_tables* T, int nfun, int solver, const double* const* qvals, double* const* out)
+{
+  return guarded(
+      [&]
+      {
+        auto msh = make_mesh(mesh);
+        const int nc = mesh->ncell, ndg = T->ndg, nq = T->nq;
+        basix::FiniteElement dg
+            = basix::element::create_lagrange(basix::cell::type::triangle, T->p, basix::element::lagrange_variant::equispaced, true);
+        if (dg.dim() != ndg)
+          throw std::runtime_error("ref_local_solver: DG dimension mismatch");
+        std::vector<std::int32_t> ident_dg((size_t)nc * ndg), ident_q((size_t)nc * nq);
+        for (size_t i = 0; i < ident_dg.size(); ++i)
+          ident_dg[i] = (std::int32_t)i;
+        for (size_t i = 0; i < ident_q.size(); ++i)
+          ident_q[i] = (std::int32_t)i;
+        auto V_dg = std::make_shared<fem::FunctionSpace>(
+            msh, std::make_shared<const fem::FiniteElement>(dg, 1),
+            std::make_shared<const fem::DofMap>(AL::regular(ident_dg.data(), nc, ndg), nc * ndg, 1, fem::ElementDofLayout(dg.entity_dofs())));
+        // "quadrature element": one value per quadrature point and cell
+        auto el_q = std::make_shared<fem::FiniteElement>(dg, 1);
+        el_q->set_space_dimension(nq);
+        auto V_q = std::make_shared<fem::FunctionSpace>(
+            msh, el_q, std::make_shared<const fem::DofMap>(AL::regular(ident_q.data(), nc, nq), nc * nq, 1, fem::ElementDofLayout(dg.entity_dofs())));
+        auto detJ = [](const double* x) { return (x[3] - x[0]) * (x[7] - x[1]) - (x[6] - x[0]) * (x[4] - x[1]); };
+        using kern_t = fem::Form<double>::kernel_t;
+        kern_t ka = [T, ndg, nq, detJ](double* A, const double*, const double*, const double* x, const int*, const std::uint8_t*)
+        {
+          const double d = std::fabs(detJ(x));
+          for (int q = 0; q < nq; ++q)
+            for (int i = 0; i < ndg; ++i)
+              for (int j = 0; j < ndg; ++j)
+                A[i * ndg + j] += d * T->qwts[q] * T->dg_q[(size_t)q * ndg + i] * T->dg_q[(size_t)q * ndg + j];
+        };
+        kern_t kl = [T, ndg, nq, detJ](double* L, const double* w, const double*, const double* x, const int*, const std::uint8_t*)
+        {
+          const double d = std::fabs(detJ(x));
+          for (int q = 0; q < nq; ++q)
+            for (int i = 0; i < ndg; ++i)
+              L[i] += d * T->qwts[q] * w[q] * T->dg_q[(size_t)q * ndg + i];
+        };
+        fem::Form<double> a({V_dg, V_dg}, ka, {}, {}, msh);
+        std::vector<std::shared_ptr<const fem::Form<double>>> l;
+        std::vector<std::shared_ptr<fem::Function<double>>> sol;
+        for (int i = 0; i < nfun; ++i)
+        {
+          auto data = std::make_shared<fem::Function<double>>(
+              V_q, std::make_shared<la::Vector<double>>(const_cast<double*>(qvals[i]), (size_t)nc * nq));
+          std::vector<std::shared_ptr<const fem::Function<double>>> cf{data};
+          l.push_back(std::make_shared<const fem::Form<double>>(std::vector<std::shared_ptr<const fem::FunctionSpace>>{V_dg}, kl, cf,
+                                                                std::vector<std::shared_ptr<const fem::Constant<double>>>{}, msh));
+          sol.push_back(std::make_shared<fem::Function<double>>(V_dg, std::make_shared<la::Vector<double>>(out[i], (size_t)nc * ndg)));
+        }
+        if (solver == 0)
+          eqlb::base::local_solver_lu<double>(sol, a, l);
+        else if (solver == 1)
+          eqlb::base::local_solver_cholesky<double>(sol, a, l);
+        else
+          eqlb::base::local_solver_cg<double>(sol, a, l);
       });
 }
 }

@@ -421,6 +421,7 @@ public:
     return n;
   }
   const std::vector<std::int32_t>& cell_domains(int) const { return _cells; }
+  std::vector<int> integral_ids(IntegralType t) const { return t == IntegralType::cell ? std::vector<int>{-1} : std::vector<int>{}; }
   const std::vector<std::int32_t>& exterior_facet_domains(int) const { return _none; }
   const std::vector<std::int32_t>& interior_facet_domains(int) const { return _none; }
 
@@ -439,6 +440,25 @@ std::map<std::pair<IntegralType, int>, std::pair<std::vector<T>, int>> allocate_
   std::map<std::pair<IntegralType, int>, std::pair<std::vector<T>, int>> out;
   const int cstride = form.coefficient_offsets().back();
   out[{IntegralType::cell, -1}] = {std::vector<T>(form.cell_domains(-1).size() * (std::size_t)cstride), cstride};
+  return out;
+}
+
+template <typename T>
+std::vector<T> pack_constants(const Form<T>& form)
+{
+  std::vector<T> out;
+  for (auto& c : form.constants())
+    out.insert(out.end(), c->value.begin(), c->value.end());
+  return out;
+}
+
+template <typename T>
+std::map<std::pair<IntegralType, int>, std::pair<std::span<const T>, int>>
+make_coefficients_span(const std::map<std::pair<IntegralType, int>, std::pair<std::vector<T>, int>>& coeffs)
+{
+  std::map<std::pair<IntegralType, int>, std::pair<std::span<const T>, int>> out;
+  for (auto& [key, val] : coeffs)
+    out[key] = {std::span<const T>(val.first), val.second};
   return out;
 }
 

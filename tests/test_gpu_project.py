@@ -22,6 +22,13 @@ def test_local_projection_parity(k):
     got = eqlb.local_projection(prob, qv)
     for a, b in zip(got, ref):
         assert np.abs(a - b).max() < 1e-12 * max(1.0, np.abs(b).max())
+    # ... and against the reference's own element loop / solvers (`base::local_solver_*`, oracle/_ref)
+    from oracle import pyref as pr
+
+    if pr.available():
+        for solver in ("lu", "cholesky", "cg"):
+            for a, b in zip(got, pr.local_solver(m, T, qv, solver)):
+                assert np.abs(a - b).max() < 1e-12 * max(1.0, np.abs(b).max())
 
 
 def test_projection_reproduces_polynomials():

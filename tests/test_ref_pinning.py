@@ -204,3 +204,21 @@ def test_oracle_matches_reference_on_unstructured_mesh(n, scramble, k):
         for x, y in zip(so, sr):
             assert np.abs(x - y).max() < 1e-11 * np.abs(y).max()
         assert np.abs(ko - kr).max() < 1e-13 * np.abs(kr).max()
+
+
+@needs_ref
+@pytest.mark.parametrize("solver", ["lu", "cholesky", "cg"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_oracle_projection_matches_reference_local_solver(k, solver):
+    """a16: the cell-wise projector against the reference's `base::local_solver_{lu,cholesky,cg}` (its element loop,
+    solver and scatter; the two FFCx cell kernels of the fixed projection forms restated in oracle/ref_driver.cpp)"""
+    from dolfinx_eqlb_b200 import tables as tb
+    from oracle import pyoracle as po
+
+    m = make_mesh("crossed", 5, 3, perturb=0.25)
+    T = tb.make_tables(k)
+    rng = np.random.default_rng(k)
+    qvals = [rng.standard_normal(m.ncell * T.nq) for _ in range(3)]
+    a, b = po.local_project(m, T, qvals), pr.local_solver(m, T, qvals, solver)
+    for x, y in zip(a, b):
+        assert np.abs(x - y).max() < 1e-12 * np.abs(y).max()

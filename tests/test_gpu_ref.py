@@ -149,3 +149,46 @@ def test_unstructured_mesh_vs_reference(n, scramble, k):
             for r in range(2):
                 assert rel_err(es.list_flux[r], sref[r]) < RTOL
             assert rel_err(es.get_korn_constants(), np.sqrt(kref)) < 1e-12
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_unstructured_cases_vs_reference(seed):
+    """seeded random cases: Delaunay mesh size, vertex scrambling, degree, number of RHS and their traction sides are
+    drawn at random; SE + EV (+ stress for k >= 2) against the reference's compiled code"""
+    from oracle import pyoracle as po
+    from test_gpu_stress import elasticity_case
+    from dolfinx_eqlb_b200 import mesh as ms
+
+    rng = np.random.default_rng(1000 + seed)
+    nb = int(rng.integers(5, 14))
+    m = ms.delaunay_unit_square(nb, seed=int(rng.integers(0, 10_000)), scramble_seed=int(rng.integers(0, 100)))
+    k = int(rng.integers(1, 4))
+    sets = [sorted(rng.choice([1, 2, 3, 4], size=int(rng.integers(0, 4)), replace=False).tolist()) for _ in range(int(rng.integers(1, 4)))]
+    case = PoissonCase(m, k, sets, seed=seed, galerkin=False)
+    ref = pr.se_run(m, case.T, case.oracle_bc(), case.G, case.F)
+    eq = eqlb.FluxEqlbSE(k, m, case.F, case.G)
+    eq.set_boundary_conditions(case.list_bfct_prime, case.list_bcs, device=bool(seed % 2))
+    eq.equilibrate_fluxes()
+    for r in range(case.nrhs):
+        assert rel_err(eq.list_flux[r], ref[r]) < RTOL, (nb, k, sets)
+    caseh = PoissonCase(m, k, sets, seed=seed, hom=True, galerkin=False)
+    ref = pr.ev_run(m, caseh.T, caseh.oracle_bc(), caseh.G, caseh.F)
+    ev = eqlb.FluxEqlbEV(k, m, caseh.F, caseh.G)
+    ev.set_boundary_conditions(caseh.list_bfct_prime, caseh.list_bcs)
+    ev.equilibrate_fluxes()
+    for r in range(caseh.nrhs):
+        assert rel_err(ev.list_flux[r], ref[r]) < RTOL, (nb, k, sets)
+    if k >= 2:
+        T, G, f, bfp, bcs, neu = elasticity_case(m, k, sets[0], seed=seed, galerkin=False)
+        bd = eqlb.boundarydata(bcs, m, T, bfp, True)
+        bc = po.BCData(bd.facet_type, bd.bflux, bd.local_fct_id, bd.node_on_stress_bnd)
+        try:
+            sref, kref = pr.se_run(m, T, bc, G, f, stress=True, korn=True)
+        except RuntimeError:
+            return  # layout the reference refuses on this mesh
+        es = eqlb.FluxEqlbSE(k, m, f, G, equilibrate_stress=True, estimate_korn_constant=True)
+        es.set_boundary_conditions(bfp, bcs)
+        es.equilibrate_fluxes()
+        for r in range(2):
+            assert rel_err(es.list_flux[r], sref[r]) < RTOL, (nb, k, sets)
+        assert rel_err(es.get_korn_constants(), np.sqrt(kref)) < 1e-12

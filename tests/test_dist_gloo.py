@@ -109,3 +109,71 @@ def test_crossed_strip_parts_tile_the_stacked_mesh():
         interior = (x[:, 0] > 0) & (x[:, 0] < 1) & (x[:, 1] > 0) & (x[:, 1] < world)
         sel = p.node_owned.astype(bool) & interior
         assert (nc[sel] == nf[sel]).all()
+
+
+def _worker_rows(rank, world, port, cfg, out):
+    """strong-scaling partition of bench.py's configs 2-4 (`dist.crossed_rows`: the global n x n mesh cut into strips
+    of rows) with the boundary data restricted to the local facets - the CPU twin of `bench.halo_check`"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    from dolfinx_eqlb_b200 import eqlb
+    from oracle import pyoracle as po
+
+    C = bench.CONFIGS[cfg]
+    k, nrhs, stress = C["k"], C["nrhs"], C["stress"]
+    T = tb.make_tables(k)
+    n = 4 * world
+    gm = ms.crossed_unit_square(n)
+    G, F = bench.synthetic_inputs(gm.ncell, T.ndg, nrhs, seed=11)
+    gbf, gbc = bench.boundary_conditions(gm, T, nrhs, list(C["neumann"]), seed=13)
+    gbd = eqlb.boundarydata(gbc, gm, T, gbf, stress)
+    ref = po.se_run(gm, T, po.BCData(gbd.facet_type, gbd.bflux, gbd.local_fct_id, gbd.node_on_stress_bnd), G, F, stress=stress)
+    part, _ = dd.crossed_rows(n, rank, world, fast=False)
+    lm, cg = part.mesh, part.cell_gid
+    lG = [g.reshape(gm.ncell, -1)[cg].ravel() for g in G]
+    lF = [f.reshape(gm.ncell, -1)[cg].ravel() for f in F]
+    gkey = gm.fct_node[:, 0].astype(np.int64) * gm.nnode + gm.fct_node[:, 1]
+    l2g_f = np.searchsorted(gkey, part.fct_gid(gm.nnode))
+    lbf, lbc = [], []
+    for r in range(nrhs):
+        gset = np.zeros(gm.nfct, dtype=bool)
+        gset[gbf[r]] = True
+        lbf.append(np.nonzero(gset[l2g_f])[0].astype(np.int32))
+        bl = []
+        for bc in gbc[r]:
+            row = np.full(gm.nfct, -1, dtype=np.int64)
+            row[bc.facets] = np.arange(bc.facets.shape[0])
+            sel = np.nonzero(row[l2g_f] >= 0)[0].astype(np.int32)
+            if sel.size:
+                bl.append(eqlb.fluxbc(sel, bc.coeffs[row[l2g_f[sel]]]))
+        lbc.append(bl)
+    lbd = eqlb.boundarydata(lbc, lm, T, lbf, stress)
+    got = po.se_run(lm, T, po.BCData(lbd.facet_type, lbd.bflux, lbd.local_fct_id, lbd.node_on_stress_bnd), lG, lF, stress=stress,
+                    node_owned=part.node_owned)
+    loc, gid = dd.se_dof_gids(part, T.nrt)
+    xs = [torch.from_numpy(np.ascontiguousarray(s)) for s in got]
+    hx = dd.HaloExchange(loc, gid)
+    hx.apply(xs)
+    live_c = part.node_owned[lm.cell_node].any(axis=1)
+    err = 0.0
+    for r in range(nrhs):
+        want = ref[r].reshape(gm.ncell, T.nrt)[cg]
+        d = np.abs(xs[r].numpy().reshape(lm.ncell, T.nrt) - want)[live_c]
+        err = max(err, float(d.max() / np.abs(want).max()))
+    out[rank] = err
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4])
+def test_strong_scaling_partition_equals_serial(cfg):
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_rows, args=(world, port, cfg, out), nprocs=world, join=True)
+        res = dict(out)
+    assert len(res) == world
+    for e in res.values():
+        assert e < 1e-12
